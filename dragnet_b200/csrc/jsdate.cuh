@@ -1,0 +1,132 @@
+/*
+ * jsdate.cuh: Date.parse for the ECMAScript date-time string format
+ * (ES5 15.9.1.15), as the reference's Datetime parser stage applies it to
+ * `date` fields (lib/stream-synthetic.js:65: `parsed = Date.parse(val)`).
+ *
+ * Grammar: YYYY | YYYY-MM | YYYY-MM-DD | +-YYYYYY-..., optionally followed by
+ * THH:mm | THH:mm:ss | THH:mm:ss.s+ and optionally Z | +-HH:mm.  No offset
+ * means UTC.  Anything else is NaN (the reference then counts `baddate`).
+ * V8's legacy free-form fallback is not restated (unpinned).
+ */
+#ifndef DNG_JSDATE_CUH
+#define DNG_JSDATE_CUH
+
+#include "jsnum.cuh"
+
+namespace dng {
+
+DNG_HD bool dd2(const uint8_t *p, int &v)
+{
+	if (p[0] < '0' || p[0] > '9' || p[1] < '0' || p[1] > '9')
+		return false;
+	v = (p[0] - '0') * 10 + (p[1] - '0');
+	return true;
+}
+
+DNG_HD int64_t days_from_civil(int64_t y, int m, int d)
+{
+	y -= m <= 2;
+	int64_t era = (y >= 0 ? y : y - 399) / 400;
+	int64_t yoe = y - era * 400;
+	int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+	int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+	return era * 146097 + doe - 719468;
+}
+
+/* returns true and *ms on success; false for NaN */
+DNG_HD bool dng_date_parse(const uint8_t *p, int n, int64_t *ms)
+{
+	int i = 0;
+	int64_t y = 0;
+	int ysign = 0, ydig = 4;
+	if (n >= 1 && (p[0] == '+' || p[0] == '-')) {
+		ysign = p[0] == '-' ? -1 : 1;
+		ydig = 6;
+		i = 1;
+	}
+	if (n - i < ydig)
+		return false;
+	for (int k = 0; k < ydig; k++, i++) {
+		if (p[i] < '0' || p[i] > '9')
+			return false;
+		y = y * 10 + (p[i] - '0');
+	}
+	if (ysign < 0) {
+		if (y == 0)
+			return false;	/* -000000 is not allowed */
+		y = -y;
+	}
+	int mo = 1, dd = 1, hh = 0, mi = 0, ss = 0, msec = 0;
+	if (i < n && p[i] == '-') {
+		if (n - i < 3 || !dd2(p + i + 1, mo))
+			return false;
+		i += 3;
+		if (i < n && p[i] == '-') {
+			if (n - i < 3 || !dd2(p + i + 1, dd))
+				return false;
+			i += 3;
+		}
+	}
+	int64_t off = 0;
+	if (i < n && p[i] == 'T') {
+		if (n - i < 6 || !dd2(p + i + 1, hh) || p[i + 3] != ':' ||
+		    !dd2(p + i + 4, mi))
+			return false;
+		i += 6;
+		if (i < n && p[i] == ':') {
+			if (n - i < 3 || !dd2(p + i + 1, ss))
+				return false;
+			i += 3;
+			if (i < n && p[i] == '.') {
+				i++;
+				int nd = 0;
+				while (i < n && p[i] >= '0' && p[i] <= '9') {
+					if (nd < 3)
+						msec = msec * 10 + (p[i] - '0');
+					nd++;
+					i++;
+				}
+				if (nd == 0)
+					return false;
+				for (; nd < 3; nd++)
+					msec *= 10;
+			}
+		}
+		if (i < n && p[i] == 'Z') {
+			i++;
+		} else if (i < n && (p[i] == '+' || p[i] == '-')) {
+			int oh, om;
+			if (n - i < 6 || !dd2(p + i + 1, oh) ||
+			    p[i + 3] != ':' || !dd2(p + i + 4, om))
+				return false;
+			if (oh > 23 || om > 59)
+				return false;
+			off = (int64_t)(oh * 60 + om) * 60000;
+			if (p[i] == '-')
+				off = -off;
+			i += 6;
+		}
+	}
+	if (i != n)
+		return false;
+	if (mo < 1 || mo > 12 || dd < 1)
+		return false;
+	int leap = (y % 4 == 0) && (y % 100 != 0 || y % 400 == 0);
+	int dim = mo == 2 ? (leap ? 29 : 28) :
+	    (mo == 4 || mo == 6 || mo == 9 || mo == 11) ? 30 : 31;
+	if (dd > dim)
+		return false;
+	if (hh > 24 || mi > 59 || ss > 59)
+		return false;
+	if (hh == 24 && (mi || ss || msec))
+		return false;
+	int64_t t = days_from_civil(y, mo, dd) * 86400000ll +
+	    ((int64_t)(hh * 60 + mi) * 60 + ss) * 1000 + msec - off;
+	if (t > 8640000000000000ll || t < -8640000000000000ll)
+		return false;
+	*ms = t;
+	return true;
+}
+
+} /* namespace dng */
+#endif

@@ -1,0 +1,705 @@
+/*
+ * plan.cpp: host-side plan compiler (plan JSON -> DevPlan).
+ *
+ * Restates, for the device, what the reference does when it assembles a scan:
+ *   lib/stream-scan.js:56-86      stage order; dn_ts synthetic + time filter
+ *   lib/datasource-file.js:154-163 datasource filter in front
+ *   lib/dragnet-impl.js:66-125    decomps = breakdown NAMES; time-bounds filter
+ *   lib/stream-synthetic.js:37-85 synthetic fields are assigned onto the
+ *                                 record, so later stages see them first
+ *   jsprim.pluck                  whole key first, then split at FIRST dot
+ */
+#include "plan.h"
+#include "jsnum.cuh"
+#include "../../include/dragnet_gpu.h"
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+
+using namespace dng;
+
+namespace {
+
+/* ---- a very small JSON DOM (host only; plans are tiny) ---------------- */
+struct JVal {
+	enum K { NUL, BOOL, NUM, STR, ARR, OBJ } k = NUL;
+	bool b = false;
+	double num = 0;
+	std::string str;
+	std::vector<JVal> arr;
+	std::vector<std::pair<std::string, JVal>> obj;	/* insertion order */
+
+	const JVal *get(const char *key) const {
+		const JVal *r = nullptr;
+		for (auto &kv : obj)
+			if (kv.first == key)
+				r = &kv.second;	/* last duplicate wins */
+		return r;
+	}
+};
+
+struct JParser {
+	const char *p, *end;
+	std::string err;
+
+	void ws() {
+		while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' ||
+		    *p == '\r'))
+			p++;
+	}
+	bool fail(const char *m) {
+		if (err.empty())
+			err = m;
+		return false;
+	}
+	static void utf8(std::string &s, unsigned cp) {
+		if (cp < 0x80) {
+			s += (char)cp;
+		} else if (cp < 0x800) {
+			s += (char)(0xC0 | (cp >> 6));
+			s += (char)(0x80 | (cp & 0x3F));
+		} else if (cp < 0x10000) {
+			s += (char)(0xE0 | (cp >> 12));
+			s += (char)(0x80 | ((cp >> 6) & 0x3F));
+			s += (char)(0x80 | (cp & 0x3F));
+		} else {
+			s += (char)(0xF0 | (cp >> 18));
+			s += (char)(0x80 | ((cp >> 12) & 0x3F));
+			s += (char)(0x80 | ((cp >> 6) & 0x3F));
+			s += (char)(0x80 | (cp & 0x3F));
+		}
+	}
+	bool hex4(unsigned &v) {
+		if (end - p < 4)
+			return fail("bad \\u escape");
+		v = 0;
+		for (int i = 0; i < 4; i++) {
+			int c = *p++, d;
+			if (c >= '0' && c <= '9') d = c - '0';
+			else if ((c | 0x20) >= 'a' && (c | 0x20) <= 'f')
+				d = (c | 0x20) - 'a' + 10;
+			else return fail("bad \\u escape");
+			v = v * 16 + d;
+		}
+		return true;
+	}
+	bool string(std::string &out) {
+		if (p >= end || *p != '"')
+			return fail("expected string");
+		p++;
+		while (p < end && *p != '"') {
+			unsigned char c = *p++;
+			if (c < 0x20)
+				return fail("control character in string");
+			if (c != '\\') {
+				out += (char)c;
+				continue;
+			}
+			if (p >= end)
+				return fail("unterminated string");
+			char e = *p++;
+			switch (e) {
+			case '"': out += '"'; break;
+			case '\\': out += '\\'; break;
+			case '/': out += '/'; break;
+			case 'b': out += '\b'; break;
+			case 'f': out += '\f'; break;
+			case 'n': out += '\n'; break;
+			case 'r': out += '\r'; break;
+			case 't': out += '\t'; break;
+			case 'u': {
+				unsigned cp, lo;
+				if (!hex4(cp))
+					return false;
+				if (cp >= 0xD800 && cp < 0xDC00 && end - p >= 6 &&
+				    p[0] == '\\' && p[1] == 'u') {
+					const char *save = p;
+					p += 2;
+					if (!hex4(lo))
+						return false;
+					if (lo >= 0xDC00 && lo < 0xE000)
+						cp = 0x10000 + ((cp - 0xD800) << 10) +
+						    (lo - 0xDC00);
+					else
+						p = save;
+				}
+				utf8(out, cp);
+				break;
+			}
+			default:
+				return fail("bad escape");
+			}
+		}
+		if (p >= end)
+			return fail("unterminated string");
+		p++;
+		return true;
+	}
+	bool value(JVal &v, int depth) {
+		if (depth > 64)
+			return fail("plan nested too deeply");
+		ws();
+		if (p >= end)
+			return fail("unexpected end of plan");
+		char c = *p;
+		if (c == '{') {
+			v.k = JVal::OBJ;
+			p++;
+			ws();
+			if (p < end && *p == '}') { p++; return true; }
+			for (;;) {
+				ws();
+				std::string key;
+				if (!string(key))
+					return false;
+				ws();
+				if (p >= end || *p != ':')
+					return fail("expected ':'");
+				p++;
+				JVal child;
+				if (!value(child, depth + 1))
+					return false;
+				v.obj.emplace_back(std::move(key), std::move(child));
+				ws();
+				if (p < end && *p == ',') { p++; continue; }
+				if (p < end && *p == '}') { p++; return true; }
+				return fail("expected ',' or '}'");
+			}
+		}
+		if (c == '[') {
+			v.k = JVal::ARR;
+			p++;
+			ws();
+			if (p < end && *p == ']') { p++; return true; }
+			for (;;) {
+				JVal child;
+				if (!value(child, depth + 1))
+					return false;
+				v.arr.push_back(std::move(child));
+				ws();
+				if (p < end && *p == ',') { p++; continue; }
+				if (p < end && *p == ']') { p++; return true; }
+				return fail("expected ',' or ']'");
+			}
+		}
+		if (c == '"') {
+			v.k = JVal::STR;
+			return string(v.str);
+		}
+		if (end - p >= 4 && !strncmp(p, "true", 4)) {
+			v.k = JVal::BOOL; v.b = true; p += 4; return true;
+		}
+		if (end - p >= 5 && !strncmp(p, "false", 5)) {
+			v.k = JVal::BOOL; v.b = false; p += 5; return true;
+		}
+		if (end - p >= 4 && !strncmp(p, "null", 4)) {
+			v.k = JVal::NUL; p += 4; return true;
+		}
+		const char *s = p;
+		if (p < end && *p == '-') p++;
+		if (p >= end || *p < '0' || *p > '9')
+			return fail("unexpected token in plan");
+		if (*p == '0') p++;
+		else while (p < end && *p >= '0' && *p <= '9') p++;
+		if (p < end && *p == '.') {
+			p++;
+			if (p >= end || *p < '0' || *p > '9')
+				return fail("bad number");
+			while (p < end && *p >= '0' && *p <= '9') p++;
+		}
+		if (p < end && (*p == 'e' || *p == 'E')) {
+			p++;
+			if (p < end && (*p == '+' || *p == '-')) p++;
+			if (p >= end || *p < '0' || *p > '9')
+				return fail("bad number");
+			while (p < end && *p >= '0' && *p <= '9') p++;
+		}
+		v.k = JVal::NUM;
+		v.num = dng_parse_decimal((const uint8_t *)s, (int)(p - s));
+		return true;
+	}
+};
+
+/* ---- compiler --------------------------------------------------------- */
+
+struct Compiler {
+	DevPlan &P;
+	std::string err;
+	int code = DNG_OK;
+	size_t pool_used = 0;
+
+	struct PathRec { std::string field; int slot0; int ncomp; };
+	std::vector<PathRec> paths;		/* unique field strings */
+	std::map<std::string, int> ctx_by_prefix;
+	struct CandRec { std::string key; int term_slot; int child_ctx; };
+	std::vector<std::vector<CandRec>> ctx_cands;
+	std::vector<int> ctx_parent, ctx_depth;
+	std::vector<std::pair<int, int>> pathinfo;	/* (path idx, nlevels) */
+	std::vector<std::string> syn_names;
+	int fields_ctx = 0;
+
+	explicit Compiler(DevPlan &p) : P(p) {}
+
+	bool fail(int c, const std::string &m) {
+		if (code == DNG_OK) {
+			code = c;
+			err = m;
+		}
+		return false;
+	}
+
+	int pool_add(const std::string &s) {
+		if (pool_used + s.size() > POOL_BYTES) {
+			fail(DNG_ELIMIT, "plan constant pool exhausted");
+			return 0;
+		}
+		int off = (int)pool_used;
+		memcpy(P.pool + pool_used, s.data(), s.size());
+		pool_used += s.size();
+		return off;
+	}
+
+	int new_ctx(const std::string &prefix, int parent, int depth) {
+		auto it = ctx_by_prefix.find(prefix);
+		if (it != ctx_by_prefix.end())
+			return it->second;
+		int id = (int)ctx_cands.size();
+		ctx_by_prefix[prefix] = id;
+		ctx_cands.emplace_back();
+		ctx_parent.push_back(parent);
+		ctx_depth.push_back(depth);
+		return id;
+	}
+
+	CandRec &cand(int ctx, const std::string &key) {
+		for (auto &c : ctx_cands[ctx])
+			if (c.key == key)
+				return c;
+		ctx_cands[ctx].push_back(CandRec{key, -1, -1});
+		return ctx_cands[ctx].back();
+	}
+
+	/* register a JSON field path; returns index into `paths` */
+	int add_path(const std::string &field) {
+		for (size_t i = 0; i < paths.size(); i++)
+			if (paths[i].field == field)
+				return (int)i;
+		std::vector<std::string> comps;
+		size_t a = 0;
+		for (;;) {
+			size_t d = field.find('.', a);
+			if (d == std::string::npos) {
+				comps.push_back(field.substr(a));
+				break;
+			}
+			comps.push_back(field.substr(a, d - a));
+			a = d + 1;
+		}
+		int L = (int)comps.size();
+		if (L > MAX_LEVELS) {
+			fail(DNG_ELIMIT, "field \"" + field + "\" has too many "
+			    "dot-separated components");
+			return 0;
+		}
+		int slot0 = 0;
+		for (auto &p : paths)
+			slot0 += p.ncomp;
+		if (slot0 + L > MAX_SLOTS - 2) {
+			fail(DNG_ELIMIT, "too many distinct fields in one scan");
+			return 0;
+		}
+		/* level l: inside context for prefix comps[0..l) */
+		std::string prefix = "\x01";	/* fields root marker */
+		int ctx = fields_ctx;
+		size_t pos = 0;
+		for (int l = 0; l < L; l++) {
+			std::string suffix = field.substr(pos);
+			cand(ctx, suffix).term_slot = slot0 + l;
+			if (l < L - 1) {
+				prefix += comps[l];
+				prefix += '\x02';
+				int child = new_ctx(prefix, ctx, ctx_depth[ctx] + 1);
+				cand(ctx, comps[l]).child_ctx = child;
+				ctx = child;
+			}
+			pos += comps[l].size() + 1;
+		}
+		paths.push_back(PathRec{field, slot0, L});
+		return (int)paths.size() - 1;
+	}
+
+	int add_pathinfo(int pidx, int nlevels) {
+		for (size_t i = 0; i < pathinfo.size(); i++)
+			if (pathinfo[i].first == pidx &&
+			    pathinfo[i].second == nlevels)
+				return (int)i;
+		pathinfo.emplace_back(pidx, nlevels);
+		return (int)pathinfo.size() - 1;
+	}
+
+	/*
+	 * Where does pluck(record, field) read from when the first `nsyn`
+	 * synthetic fields have been assigned onto the record?
+	 */
+	Src resolve(const std::string &field, int nsyn) {
+		Src s;
+		s.kind = SRC_UNDEF;
+		s.idx = 0;
+		for (int j = nsyn - 1; j >= 0; j--) {
+			if (syn_names[j] == field) {
+				s.kind = SRC_SYNTH;
+				s.idx = (u8)j;
+				return s;
+			}
+		}
+		int pidx = add_path(field);
+		int nlevels = paths.size() ? paths[pidx].ncomp : 0;
+		size_t d = field.find('.');
+		if (d != std::string::npos) {
+			std::string k1 = field.substr(0, d);
+			for (int j = 0; j < nsyn; j++)
+				if (syn_names[j] == k1)
+					nlevels = 1;	/* number has no props */
+		}
+		s.kind = SRC_PATH;
+		s.idx = (u8)add_pathinfo(pidx, nlevels);
+		return s;
+	}
+
+	/* krill predicate -> jump code; returns entry index or -1 if trivial */
+	struct Patch { int leaf; bool on_true; };
+
+	bool emit(const JVal &pred, int nsyn, std::vector<Leaf> &prog,
+	    std::vector<Patch> &tlist, std::vector<Patch> &flist) {
+		if (pred.k != JVal::OBJ)
+			return fail(DNG_EINVAL, "predicate is not an object");
+		if (pred.obj.empty()) {
+			Leaf lf;
+			memset(&lf, 0, sizeof (lf));
+			lf.op = OP_TRUE;
+			prog.push_back(lf);
+			tlist.push_back(Patch{(int)prog.size() - 1, true});
+			flist.push_back(Patch{(int)prog.size() - 1, false});
+			return true;
+		}
+		if (pred.obj.size() != 1)
+			return fail(DNG_EINVAL, "predicate: expected exactly one key");
+		const std::string &key = pred.obj[0].first;
+		const JVal &args = pred.obj[0].second;
+		if (key == "and" || key == "or") {
+			bool is_and = key == "and";
+			if (args.k != JVal::ARR || args.arr.empty())
+				return fail(DNG_EINVAL, "predicate: \"" + key +
+				    "\" requires a non-empty array");
+			for (size_t i = 0; i < args.arr.size(); i++) {
+				std::vector<Patch> t, f;
+				int start = (int)prog.size();
+				if (!emit(args.arr[i], nsyn, prog, t, f))
+					return false;
+				bool last = i + 1 == args.arr.size();
+				(void)start;
+				if (is_and) {
+					/* false anywhere -> whole false */
+					flist.insert(flist.end(), f.begin(), f.end());
+					if (last)
+						tlist.insert(tlist.end(), t.begin(), t.end());
+					else
+						patch(prog, t, (int)prog.size());
+				} else {
+					tlist.insert(tlist.end(), t.begin(), t.end());
+					if (last)
+						flist.insert(flist.end(), f.begin(), f.end());
+					else
+						patch(prog, f, (int)prog.size());
+				}
+			}
+			return true;
+		}
+		static const char *ops[] = { "eq", "ne", "lt", "le", "gt", "ge" };
+		int op = -1;
+		for (int i = 0; i < 6; i++)
+			if (key == ops[i])
+				op = i;
+		if (op < 0)
+			return fail(DNG_EINVAL, "predicate: unknown operator \"" +
+			    key + "\"");
+		if (args.k != JVal::ARR || args.arr.size() != 2 ||
+		    args.arr[0].k != JVal::STR)
+			return fail(DNG_EINVAL, "predicate: \"" + key +
+			    "\" requires [field, constant]");
+		const JVal &c = args.arr[1];
+		Leaf lf;
+		memset(&lf, 0, sizeof (lf));
+		lf.op = (u8)op;
+		lf.src = resolve(args.arr[0].str, nsyn);
+		if (c.k == JVal::STR) {
+			lf.cstr = 1;
+			lf.coff = (u16)pool_add(c.str);
+			lf.clen = (u16)c.str.size();
+			lf.cnum = dng_string_to_number(
+			    (const uint8_t *)c.str.data(), (int)c.str.size());
+		} else if (c.k == JVal::NUM) {
+			lf.cnum = c.num;
+		} else if (c.k == JVal::BOOL) {
+			lf.cnum = c.b ? 1.0 : 0.0;
+		} else {
+			return fail(DNG_EINVAL, "predicate: constant must be a "
+			    "string, number or boolean");
+		}
+		prog.push_back(lf);
+		tlist.push_back(Patch{(int)prog.size() - 1, true});
+		flist.push_back(Patch{(int)prog.size() - 1, false});
+		return true;
+	}
+
+	static void patch(std::vector<Leaf> &prog, std::vector<Patch> &l,
+	    int target) {
+		for (auto &p : l) {
+			if (p.on_true)
+				prog[p.leaf].jt = (int16_t)target;
+			else
+				prog[p.leaf].jf = (int16_t)target;
+		}
+		l.clear();
+	}
+
+	int compile_pred(const JVal *pred, int nsyn, std::vector<Leaf> &prog) {
+		if (!pred || pred->k == JVal::NUL)
+			return -1;
+		if (pred->k == JVal::OBJ && pred->obj.empty())
+			return -1;	/* {} is always true */
+		int entry = (int)prog.size();
+		std::vector<Patch> t, f;
+		if (!emit(*pred, nsyn, prog, t, f))
+			return -1;
+		patch(prog, t, -1);
+		patch(prog, f, -2);
+		return entry;
+	}
+
+	bool run(const JVal &root, dng_plan *out) {
+		memset(&P, 0, sizeof (P));
+		if (root.k != JVal::OBJ)
+			return fail(DNG_EINVAL, "plan must be a JSON object");
+		const JVal *fmt = root.get("format");
+		P.format = FMT_JSON;
+		if (fmt && fmt->k == JVal::STR) {
+			if (fmt->str == "json-skinner")
+				P.format = FMT_SKINNER;
+			else if (fmt->str != "json")
+				return fail(DNG_EINVAL, "unsupported format: \"" +
+				    fmt->str + "\"");
+		}
+		P.sk_fields_slot = P.sk_value_slot = -1;
+		if (P.format == FMT_SKINNER) {
+			/* envelope {fields:{...}, value:N}: lib/format-json.js:55-73 */
+			int env = new_ctx("", -1, 1);
+			fields_ctx = new_ctx("\x01", env, 2);
+			P.sk_fields_slot = MAX_SLOTS - 2;
+			P.sk_value_slot = MAX_SLOTS - 1;
+			CandRec &cf = cand(env, "fields");
+			cf.term_slot = P.sk_fields_slot;
+			cf.child_ctx = fields_ctx;
+			cand(env, "value").term_slot = P.sk_value_slot;
+		} else {
+			fields_ctx = new_ctx("\x01", -1, 1);
+		}
+		P.root_ctx = (int8_t)fields_ctx;
+
+		std::vector<Leaf> prog;
+		P.ds_entry = (int16_t)compile_pred(root.get("ds_filter"), 0, prog);
+		P.user_entry = (int16_t)compile_pred(root.get("filter"), 0, prog);
+		if (this->code != DNG_OK)
+			return false;
+
+		const JVal *syn = root.get("synthetic");
+		if (syn && syn->k == JVal::ARR) {
+			if (syn->arr.size() > MAX_SYN)
+				return fail(DNG_ELIMIT, "too many synthetic fields");
+			for (auto &s : syn->arr) {
+				const JVal *n = s.get("name"), *f = s.get("field");
+				if (!n || !f || n->k != JVal::STR ||
+				    f->k != JVal::STR)
+					return fail(DNG_EINVAL, "synthetic: need "
+					    "string \"name\" and \"field\"");
+				int j = (int)syn_names.size();
+				P.syn[j] = resolve(f->str, j);
+				syn_names.push_back(n->str);
+			}
+		}
+		P.nsyn = (u8)syn_names.size();
+
+		P.time_entry = -1;
+		const JVal *tb = root.get("time_bounds");
+		if (tb && tb->k == JVal::OBJ) {
+			const JVal *f = tb->get("field"), *ge = tb->get("ge"),
+			    *lt = tb->get("lt");
+			if (!f || f->k != JVal::STR || !ge || !lt ||
+			    ge->k != JVal::NUM || lt->k != JVal::NUM)
+				return fail(DNG_EINVAL, "time_bounds: need field, "
+				    "ge, lt");
+			/* {and:[{ge:[f,a]},{lt:[f,b]}]}: lib/dragnet-impl.js:108-119 */
+			P.time_entry = (int16_t)prog.size();
+			Leaf a, b;
+			memset(&a, 0, sizeof (a));
+			memset(&b, 0, sizeof (b));
+			a.op = OP_GE;
+			a.src = resolve(f->str, P.nsyn);
+			a.cnum = ge->num;
+			a.jt = (int16_t)(prog.size() + 1);
+			a.jf = -2;
+			b.op = OP_LT;
+			b.src = a.src;
+			b.cnum = lt->num;
+			b.jt = -1;
+			b.jf = -2;
+			prog.push_back(a);
+			prog.push_back(b);
+		}
+
+		const JVal *bds = root.get("breakdowns");
+		if (!bds || bds->k != JVal::ARR)
+			return fail(DNG_EINVAL, "plan: \"breakdowns\" must be an "
+			    "array");
+		if (bds->arr.size() > MAX_COLS)
+			return fail(DNG_ELIMIT, "too many breakdowns");
+		out->ncols = 0;
+		for (auto &b : bds->arr) {
+			const JVal *n = b.get("name");
+			if (!n || n->k != JVal::STR)
+				return fail(DNG_EINVAL, "breakdown without a name");
+			Col &c = P.col[P.ncols];
+			/* the aggregator plucks the breakdown NAME
+			 * (lib/dragnet-impl.js:79-80) */
+			c.src = resolve(n->str, P.nsyn);
+			c.kind = COL_DISCRETE;
+			c.step = 0;
+			const JVal *ag = b.get("aggr");
+			if (ag && ag->k == JVal::STR) {
+				if (ag->str == "quantize") {
+					c.kind = COL_P2;
+				} else if (ag->str == "lquantize") {
+					const JVal *st = b.get("step");
+					if (!st || st->k != JVal::NUM)
+						return fail(DNG_EINVAL, "aggr "
+						    "\"lquantize\" requires "
+						    "\"step\"");
+					c.kind = COL_LINEAR;
+					c.step = st->num;
+				} else {
+					return fail(DNG_EINVAL,
+					    "unsupported aggr: \"" + ag->str +
+					    "\"");
+				}
+			}
+			out->col_kind[P.ncols] = c.kind;
+			out->col_step[P.ncols] = c.step;
+			P.ncols++;
+		}
+		out->ncols = P.ncols;
+		if (this->code != DNG_OK)
+			return false;
+
+		/* ---- flatten ---- */
+		if (prog.size() > MAX_CODE)
+			return fail(DNG_ELIMIT, "filter too large");
+		P.ncode = (u8)prog.size();
+		for (size_t i = 0; i < prog.size(); i++)
+			P.code[i] = prog[i];
+		if (ctx_cands.size() > MAX_CTX)
+			return fail(DNG_ELIMIT, "too many nested field contexts");
+		P.nctx = (u8)ctx_cands.size();
+		int nc = 0;
+		for (size_t c = 0; c < ctx_cands.size(); c++) {
+			Ctx &x = P.ctx[c];
+			x.parent = (int8_t)ctx_parent[c];
+			x.depth = (u8)ctx_depth[c];
+			x.cand_begin = (u16)nc;
+			x.bloom = 0;
+			x.arraylike = 0;
+			for (auto &cr : ctx_cands[c]) {
+				bool idx = !cr.key.empty() &&
+				    (cr.key == "0" || cr.key[0] != '0');
+				for (unsigned char ch : cr.key)
+					if (ch < '0' || ch > '9')
+						idx = false;
+				if (idx || cr.key == "length")
+					x.arraylike = 1;
+				if (nc >= MAX_CANDS)
+					return fail(DNG_ELIMIT, "too many field "
+					    "name candidates");
+				Cand &d = P.cand[nc++];
+				d.off = (u16)pool_add(cr.key);
+				d.len = (u16)cr.key.size();
+				u32 h = 2166136261u;
+				for (unsigned char ch : cr.key)
+					h = (h ^ ch) * 16777619u;
+				d.hash = h;
+				d.term_slot = (int8_t)cr.term_slot;
+				d.child_ctx = (int8_t)cr.child_ctx;
+				x.bloom |= 1ull << (h & 63);
+			}
+			x.cand_end = (u16)nc;
+		}
+		P.ncand = (u8)nc;
+		/* subtree masks: slots reachable at or below each context */
+		for (int c = (int)ctx_cands.size() - 1; c >= 0; c--) {
+			u32 m = 0;
+			for (auto &cr : ctx_cands[c]) {
+				if (cr.term_slot >= 0)
+					m |= 1u << cr.term_slot;
+				if (cr.child_ctx >= 0)
+					m |= P.ctx[cr.child_ctx].subtree_mask;
+			}
+			P.ctx[c].subtree_mask = m;
+		}
+		if (pathinfo.size() > MAX_PATHS)
+			return fail(DNG_ELIMIT, "too many distinct fields");
+		P.npaths = (u8)pathinfo.size();
+		int nslots = 0;
+		for (auto &p : paths)
+			nslots += p.ncomp;
+		P.nslots = (u8)nslots;
+		for (size_t i = 0; i < pathinfo.size(); i++) {
+			P.path[i].slot0 = (u8)paths[pathinfo[i].first].slot0;
+			P.path[i].nlevels = (u8)pathinfo[i].second;
+		}
+		return this->code == DNG_OK;
+	}
+};
+
+} /* namespace */
+
+int dng_plan_compile(const char *json, dng_plan *out, char *err,
+    unsigned long errlen)
+{
+	JParser jp;
+	jp.p = json;
+	jp.end = json + strlen(json);
+	JVal root;
+	if (!jp.value(root, 0)) {
+		if (err && errlen)
+			snprintf(err, errlen, "invalid plan JSON: %s",
+			    jp.err.c_str());
+		return DNG_EINVAL;
+	}
+	jp.ws();
+	if (jp.p != jp.end) {
+		if (err && errlen)
+			snprintf(err, errlen, "invalid plan JSON: trailing data");
+		return DNG_EINVAL;
+	}
+	Compiler c(out->dev);
+	if (!c.run(root, out)) {
+		if (err && errlen)
+			snprintf(err, errlen, "%s", c.err.c_str());
+		return c.code != DNG_OK ? c.code : DNG_EINVAL;
+	}
+	if (err && errlen)
+		err[0] = '\0';
+	return DNG_OK;
+}

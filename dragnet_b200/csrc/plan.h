@@ -1,0 +1,130 @@
+/*
+ * plan.h: the flat, device-resident form of one scan.
+ *
+ * A dng_plan is the reference's QueryConfig (lib/dragnet.js:28-77) plus the
+ * datasource properties StreamScan needs (lib/stream-scan.js:40-94), compiled
+ * once on the host into plain arrays the scan kernel copies to shared memory:
+ *
+ *   - a trie of "contexts" for jsprim.pluck-style dotted lookups
+ *     (whole-key-first, then split at the first dot; lib/stream-synthetic.js:47),
+ *   - krill predicates as short-circuit jump code
+ *     (lib/krill-skinner-stream.js:29-52),
+ *   - synthetic date fields (lib/stream-synthetic.js:37-85),
+ *   - breakdown columns with their bucketizers (lib/dragnet.js:52-71).
+ */
+#ifndef DNG_PLAN_H
+#define DNG_PLAN_H
+
+#include <stdint.h>
+
+namespace dng {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+enum ValType : u8 {
+	T_UNDEF = 0, T_NULL = 1, T_FALSE = 2, T_TRUE = 3,
+	T_NUM = 4, T_STR = 5, T_OBJ = 6, T_ARR = 7
+};
+
+/* value flags */
+enum : u8 {
+	VF_ESCAPED = 1,		/* string contains a backslash escape */
+	VF_SIMPLEINT = 2,	/* number is [-]digits, <= 15 digits, not "-0" */
+};
+
+enum : int {
+	MAX_SLOTS = 32, MAX_CTX = 24, MAX_CANDS = 64, MAX_PATHS = 24,
+	MAX_LEVELS = 8, MAX_CODE = 64, MAX_SYN = 8, MAX_COLS = 12,
+	POOL_BYTES = 3072, KEY_MAX = 512
+};
+
+/* record flags produced by the parser */
+enum : u32 {
+	RF_INVALID = 1,		/* not valid JSON */
+	RF_SLOW = 2,		/* took a slow path (escaped key compare, ...) */
+	RF_UNSUPPORTED = 4,	/* device code cannot decide this record */
+};
+
+struct Cand {			/* a key that matters inside one context */
+	u32 hash;		/* FNV-1a of the raw key bytes */
+	u16 off, len;		/* key bytes in pool */
+	int8_t term_slot;	/* slot receiving the value, or -1 */
+	int8_t child_ctx;	/* context entered if the value is an object, or -1 */
+	u16 pad;
+};
+
+struct Ctx {
+	u64 bloom;		/* bit (hash & 63) for every candidate */
+	u32 subtree_mask;	/* slots at or below this context */
+	u16 cand_begin, cand_end;
+	int8_t parent;
+	u8 depth;		/* container depth at which this context lives */
+	u16 arraylike;		/* a candidate is "length" or an array index:
+				 * an ARRAY here would need index semantics */
+};
+
+struct PathInfo {
+	u8 slot0;		/* level l of this path uses slot slot0 + l */
+	u8 nlevels;		/* levels that may supply the value */
+	u16 pad;
+};
+
+enum SrcKind : u8 { SRC_UNDEF = 0, SRC_PATH = 1, SRC_SYNTH = 2 };
+struct Src { u8 kind; u8 idx; };
+
+enum Op : u8 { OP_EQ = 0, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_TRUE };
+
+struct Leaf {
+	double cnum;		/* ToNumber(constant) */
+	u16 coff, clen;		/* constant bytes in pool when cstr */
+	int16_t jt, jf;		/* next leaf if true/false; -1 accept, -2 reject */
+	u8 op;
+	u8 cstr;		/* constant is a string */
+	Src src;
+	u32 pad;
+};
+
+struct Col {
+	double step;
+	Src src;
+	u8 kind;		/* 0 discrete, 1 power-of-two, 2 linear */
+	u8 pad[5];
+};
+
+enum : u8 { COL_DISCRETE = 0, COL_P2 = 1, COL_LINEAR = 2 };
+enum : u8 { FMT_JSON = 0, FMT_SKINNER = 1 };
+
+struct DevPlan {
+	Leaf code[MAX_CODE];
+	Col col[MAX_COLS];
+	Ctx ctx[MAX_CTX];
+	Cand cand[MAX_CANDS];
+	PathInfo path[MAX_PATHS];
+	Src syn[MAX_SYN];
+	int16_t ds_entry, user_entry, time_entry;	/* -1 none */
+	u8 format;
+	u8 nctx, ncand, npaths, nslots, nsyn, ncols, ncode;
+	int8_t root_ctx;	/* context of the record's fields object */
+	int8_t sk_fields_slot, sk_value_slot;	/* json-skinner envelope */
+	u8 pad[3];
+	char pool[POOL_BYTES];
+};
+
+} /* namespace dng */
+
+struct dng_plan {
+	dng::DevPlan dev;
+	/* host copies for result rendering */
+	int ncols;
+	dng::u8 col_kind[dng::MAX_COLS];
+	double col_step[dng::MAX_COLS];
+};
+
+/* host-only: compile plan JSON. Returns 0 or DNG_E*, message in err. */
+int dng_plan_compile(const char *json, dng_plan *out, char *err,
+    unsigned long errlen);
+
+#endif

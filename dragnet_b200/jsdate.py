@@ -22,7 +22,7 @@ _ISO = re.compile(
 def days_from_civil(y, m, d):
     """Days since 1970-01-01 of a proleptic Gregorian date."""
     y -= m <= 2
-    era = (y if y >= 0 else y - 399) // 400
+    era = y // 400
     yoe = y - era * 400
     doy = (153 * (m + (-3 if m > 2 else 9)) + 2) // 5 + d - 1
     doe = yoe * 365 + yoe // 4 - yoe // 100 + doy
@@ -74,7 +74,7 @@ def to_iso_string(ms):
     ms = int(ms)
     days, rem = divmod(ms, 86400000)
     z = days + 719468
-    era = (z if z >= 0 else z - 146096) // 146097
+    era = z // 146097
     doe = z - era * 146097
     yoe = (doe - doe // 1460 + doe // 36524 - doe // 146096) // 365
     y = yoe + era * 400

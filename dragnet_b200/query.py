@@ -40,7 +40,8 @@ def _js_parse_int(v):
         s = _js_num_str(v)
     else:
         s = str(v)
-    s = s.lstrip(' \t\n\r\v\f ﻿')
+    s = s.lstrip(' \t\n\r\v\f\u00a0\u1680\u2000\u2001\u2002\u2003\u2004\u2005'
+                 '\u2006\u2007\u2008\u2009\u200a\u2028\u2029\u202f\u205f\u3000\ufeff')
     i = 0
     sign = 1
     if i < len(s) and s[i] in '+-':

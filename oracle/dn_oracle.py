@@ -35,7 +35,8 @@ import re
 
 UNDEF = type('Undefined', (), {'__repr__': lambda s: 'undefined'})()
 
-JS_WS = ' \t\n\r\v\f             　  ﻿'
+JS_WS = (' \t\n\r\v\f\u00a0\u1680\u2000\u2001\u2002\u2003\u2004\u2005'
+         '\u2006\u2007\u2008\u2009\u200a\u2028\u2029\u202f\u205f\u3000\ufeff')
 
 
 # --------------------------------------------------------------------------
@@ -340,7 +341,7 @@ _ISO = re.compile(
 
 def _days_from_civil(y, m, d):
     y -= m <= 2
-    era = (y if y >= 0 else y - 399) // 400
+    era = y // 400
     yoe = y - era * 400
     doy = (153 * (m + (-3 if m > 2 else 9)) + 2) // 5 + d - 1
     doe = yoe * 365 + yoe // 4 - yoe // 100 + doy

@@ -1,0 +1,153 @@
+"""Scan engines the parity tests can drive with the golden harness.
+
+  py_engine         oracle/dn_oracle.py
+  hostcheck_engine  tests/hostcheck/hostcheck: the device per-record code
+                    (dragnet_b200/csrc/record.cuh) compiled for the host,
+                    TEST ONLY
+"""
+
+import json
+import math
+import os
+import struct
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import dn_oracle  # noqa: E402
+
+HOSTCHECK_DIR = os.path.join(ROOT, 'tests', 'hostcheck')
+CSRC = os.path.join(ROOT, 'dragnet_b200', 'csrc')
+
+
+def py_engine(plan, files):
+    def chunks():
+        for p in files:
+            with open(p, 'rb') as f:
+                while True:
+                    b = f.read(16834)   # lib/datasource-file.js:264
+                    if not b:
+                        break
+                    yield b
+    return dn_oracle.scan(plan, chunks())
+
+
+def build_hostcheck():
+    exe = os.path.join(HOSTCHECK_DIR, 'hostcheck')
+    srcs = [os.path.join(HOSTCHECK_DIR, 'hostcheck.cpp'),
+            os.path.join(CSRC, 'plan.cpp'), os.path.join(CSRC, 'result.cpp')]
+    deps = srcs + [os.path.join(CSRC, n) for n in
+                   ('record.cuh', 'jsnum.cuh', 'jsdate.cuh', 'plan.h',
+                    'result.h')]
+    if not os.path.exists(exe) or \
+            os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(['g++', '-std=c++17', '-O1', '-g', '-o', exe] +
+                              srcs)
+    return exe
+
+
+COUNTER_MAP = [
+    # (stage, counter, key in flat counters)
+    ('json parser', 'invalid json', 'invalid_json'),
+    ('json parser', 'invalid point', 'invalid_point'),
+    ('Datasource filter', 'nfilteredout', 'ds_filtered'),
+    ('Datasource filter', 'nfailedeval', 'ds_failedeval'),
+    ('User filter', 'nfilteredout', 'user_filtered'),
+    ('User filter', 'nfailedeval', 'user_failedeval'),
+    ('Datetime parser', 'undef', 'synth_undef'),
+    ('Datetime parser', 'baddate', 'synth_baddate'),
+    ('Time filter', 'nfilteredout', 'time_filtered'),
+    ('Time filter', 'nfailedeval', 'time_failedeval'),
+]
+
+
+def staged_counters(plan, c, npoints):
+    """Flat drop counters (dng_counters) -> vstream-style per-stage counters
+    (bin/dn:911-916), by walking the pipeline in stage order."""
+    out = {}
+
+    def put(stage, name, n):
+        if n:
+            out.setdefault(stage, {})[name] = n
+
+    n = c['lines']
+    put('json parser', 'ninputs', n)
+    put('json parser', 'invalid json', c['invalid_json'])
+    n -= c['invalid_json']
+    put('json parser', 'noutputs', n)
+    if plan.get('format', 'json') == 'json':
+        put('SkinnerAdapterStream', 'ninputs', n)
+        put('SkinnerAdapterStream', 'noutputs', n)
+    else:
+        put('json parser', 'invalid point', c.get('invalid_point', 0))
+        n -= c.get('invalid_point', 0)
+
+    def filt(stage, present, kf, ke):
+        nonlocal n
+        if not present:
+            return
+        put(stage, 'ninputs', n)
+        put(stage, 'nfilteredout', c[kf])
+        put(stage, 'nfailedeval', c[ke])
+        n -= c[kf] + c[ke]
+        put(stage, 'noutputs', n)
+
+    filt('Datasource filter', plan.get('ds_filter'), 'ds_filtered',
+         'ds_failedeval')
+    filt('User filter', plan.get('filter'), 'user_filtered',
+         'user_failedeval')
+    if plan.get('synthetic'):
+        put('Datetime parser', 'ninputs', n)
+        put('Datetime parser', 'undef', c['synth_undef'])
+        put('Datetime parser', 'baddate', c['synth_baddate'])
+        n -= c['synth_undef'] + c['synth_baddate']
+        put('Datetime parser', 'noutputs', n)
+    filt('Time filter', plan.get('time_bounds'), 'time_filtered',
+         'time_failedeval')
+    assert n == c['aggr'], (n, c)
+    put('Aggregator', 'ninputs', n)
+    put('Aggregator', 'noutputs', npoints)
+    return out
+
+
+def hostcheck_engine(plan, files):
+    exe = build_hostcheck()
+    with tempfile.NamedTemporaryFile('w', suffix='.json', delete=False) as f:
+        json.dump(plan, f)
+        pf = f.name
+    try:
+        out = subprocess.run([exe, pf] + list(files), capture_output=True,
+                             check=True).stdout
+    finally:
+        os.unlink(pf)
+    doc = json.loads(out)
+    assert doc['counters']['unsupported'] == 0, doc['counters']
+    points = []
+    for p in doc['points']:
+        fields = []
+        for b, col in zip(plan['breakdowns'], p['cols']):
+            if 's' in col:
+                fields.append((b['name'], bytes.fromhex(col['s'])))
+            else:
+                fields.append((b['name'], struct.unpack(
+                    '<d', struct.pack('<Q', int(col['n'], 16)))[0]))
+        points.append((fields, p['value']))
+    return points, staged_counters(plan, doc['counters'], len(points))
+
+
+def canon_points(points):
+    """Order-independent, NaN-safe form for comparing two engines."""
+    out = []
+    for fields, value in points:
+        key = []
+        for name, v in fields:
+            if isinstance(v, bytes):
+                key.append(('s', v))
+            elif v != v:
+                key.append(('n', 'nan'))
+            else:
+                key.append(('n', float(v) + 0.0))
+        out.append((tuple(key), value))
+    return sorted(out, key=repr)

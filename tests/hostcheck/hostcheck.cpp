@@ -1,0 +1,117 @@
+/*
+ * hostcheck: TEST-ONLY host build of the per-record device logic
+ * (dragnet_b200/csrc/record.cuh) so that it can be checked against oracle/
+ * in this GPU-less container before a gpurun.  It is NOT part of
+ * libdragnet_gpu.so, is never installed and is not a CPU fallback: the
+ * product has no host execution path.
+ *
+ *   hostcheck PLAN.json FILE...   -> one JSON document on stdout
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../dragnet_b200/csrc/record.cuh"
+#include "../../dragnet_b200/csrc/result.h"
+#include "../../include/dragnet_gpu.h"
+
+using namespace dng;
+
+static std::string slurp(const char *path)
+{
+	std::ifstream f(path, std::ios::binary);
+	std::stringstream ss;
+	ss << f.rdbuf();
+	return ss.str();
+}
+
+int main(int argc, char **argv)
+{
+	if (argc < 2) {
+		fprintf(stderr, "usage: hostcheck PLAN.json FILE...\n");
+		return 2;
+	}
+	std::string pj = slurp(argv[1]);
+	static dng_plan plan;
+	char err[256];
+	int rc = dng_plan_compile(pj.c_str(), &plan, err, sizeof (err));
+	if (rc != 0) {
+		fprintf(stderr, "plan: %s\n", err);
+		return 1;
+	}
+	std::string data;
+	for (int i = 2; i < argc; i++)
+		data += slurp(argv[i]);
+
+	LocalCounters C;
+	memset(&C, 0, sizeof (C));
+	std::map<std::string, uint64_t> table;
+	uint64_t total = 0;
+	static RecState R;
+	static u8 kbuf[KEY_MAX + 64];
+	size_t pos = 0;
+	while (pos < data.size()) {
+		size_t nl = data.find('\n', pos);
+		size_t end = nl == std::string::npos ? data.size() : nl;
+		u32 len = (u32)(end - pos);
+		const u8 *rec = (const u8 *)data.data() + pos;
+		C.lines++;
+		parse_record(rec, len, plan.dev, R);
+		if (R.flags & RF_UNSUPPORTED)
+			C.unsupported++;
+		if (R.flags & RF_INVALID) {
+			C.invalid_json++;
+		} else {
+			u32 klen;
+			u64 w;
+			if (process_record(rec, len, plan.dev, R, C, kbuf, klen,
+			    w)) {
+				table[std::string((char *)kbuf, klen)] += w;
+				total += w;
+			}
+		}
+		pos = end + 1;
+	}
+	dng_result res;
+	res.init_from_plan(&plan);
+	for (auto &kv : table) {
+		res.keys.push_back(kv.first);
+		res.values.push_back(kv.second);
+	}
+	res.finalize(total);
+	printf("{\"points\":[");
+	for (size_t i = 0; i < res.keys.size(); i++) {
+		printf("%s{\"cols\":[", i ? "," : "");
+		for (int j = 0; j < res.ncols; j++) {
+			const dng_result::Cell &c = res.cells[i * res.ncols + j];
+			if (j)
+				printf(",");
+			if (c.is_number) {
+				uint64_t b;
+				memcpy(&b, &c.num, 8);
+				printf("{\"n\":\"%016llx\"}",
+				    (unsigned long long)b);
+			} else {
+				printf("{\"s\":\"");
+				for (size_t x = 0; x < c.len; x++)
+					printf("%02x", (unsigned char)
+					    res.keys[i][c.off + x]);
+				printf("\"}");
+			}
+		}
+		printf("],\"value\":%llu}", (unsigned long long)res.values[i]);
+	}
+	printf("],\"counters\":{");
+#define CTR(n) printf("\"" #n "\":%u,", C.n)
+	CTR(lines); CTR(invalid_json); CTR(invalid_point); CTR(ds_filtered);
+	CTR(ds_failedeval); CTR(user_filtered); CTR(user_failedeval);
+	CTR(synth_undef); CTR(synth_baddate); CTR(time_filtered);
+	CTR(time_failedeval); CTR(aggr); CTR(slow);
+	printf("\"unsupported\":%u}}\n", C.unsupported);
+	return 0;
+}

@@ -1,5 +1,7 @@
-"""Pins the Python oracle (oracle/dn_oracle.py) to every `dn scan` golden the
-reference's tests hold for the raw-scan path."""
+"""The device per-record code (record.cuh, plan.cpp) compiled for the host by
+tests/hostcheck -- a TEST-ONLY harness, not a product path -- must reproduce
+every reference golden too.  This is what lets kernel logic be iterated here
+(no GPU) before the `-m gpu` parity tests run through libdragnet_gpu.so."""
 
 import os
 import sys
@@ -7,13 +9,14 @@ import sys
 import pytest
 
 sys.path.insert(0, os.path.dirname(__file__))
-from engines import py_engine  # noqa: E402
+from engines import hostcheck_engine  # noqa: E402
 from golden_harness import check_section  # noqa: E402
 
 
 @pytest.mark.parametrize('suite', ['scan_file', 'scan_fileset', 'empty',
                                    'scan_manta'])
-def test_python_oracle_matches_reference_goldens(suite, goldens, datadir):
+def test_device_record_logic_matches_reference_goldens(suite, goldens,
+                                                       datadir):
     n = 0
     for i, sec in enumerate(goldens['suites'][suite]):
         if sec['cmd'] != 'scan':
@@ -22,6 +25,6 @@ def test_python_oracle_matches_reference_goldens(suite, goldens, datadir):
                                       '--dry-run' in sec['argv'] or
                                       '-n' in sec['argv']):
             continue
-        check_section(py_engine, suite, i, sec, datadir)
+        check_section(hostcheck_engine, suite, i, sec, datadir)
         n += 1
     assert n >= 8
