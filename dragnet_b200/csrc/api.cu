@@ -1,0 +1,901 @@
+/*
+ * api.cu: the C ABI of libdragnet_gpu.so (include/dragnet_gpu.h).
+ *
+ * Host-side plumbing only: device buffers, the H2D ring that keeps PCIe busy
+ * while the previous chunk is being scanned, line carry between chunks
+ * (lstream semantics, lib/format-json.js:32-33), kernel launches, result
+ * download.  There is deliberately no host execution path for records: if no
+ * CUDA device is usable, dng_scan_open() fails.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dragnet_gpu.h"
+#include "plan.h"
+#include "result.h"
+#include "scan_kernel.cuh"
+#include "gen.cuh"
+
+using namespace dng;
+
+namespace {
+
+const size_t RING_SLOTS = 3;
+const size_t CARRY_ROOM = (size_t)DNG_MAXREC + 4096;	/* room before a chunk */
+
+size_t env_size(const char *name, size_t dflt)
+{
+	const char *v = getenv(name);
+	if (!v || !*v)
+		return dflt;
+	return (size_t)strtoull(v, nullptr, 0);
+}
+
+void set_err(char *err, size_t errlen, const char *fmt, const char *a = "")
+{
+	if (err && errlen)
+		snprintf(err, errlen, fmt, a);
+}
+
+} /* namespace */
+
+struct dng_scan {
+	dng_plan plan;
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	DevPlan *d_plan = nullptr;
+	GTable tab{};
+	unsigned long long *d_counters = nullptr;
+	unsigned long long *d_nl = nullptr;	/* find_nl scratch (2) */
+	size_t table_cap = 0;
+	/* H2D ring */
+	size_t ring_cap = 0;
+	u8 *d_ring[RING_SLOTS] = {};
+	u8 *h_stage[RING_SLOTS] = {};
+	cudaEvent_t ev_ready[RING_SLOTS] = {}, ev_free[RING_SLOTS] = {};
+	bool slot_used[RING_SLOTS] = {};
+	size_t next_slot = 0;
+	/* carry: the unterminated tail of everything fed so far */
+	u8 *d_carry = nullptr;
+	size_t carry_len = 0;
+	u8 *d_side = nullptr;		/* carry + head of a device chunk */
+	/* stats */
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;
+	std::vector<cudaEvent_t> ev_pool;
+	double kernel_ms = 0;
+	uint64_t launches = 0, kernel_bytes = 0, bytes_fed = 0;
+	bool finished = false;
+	std::string err;
+	int err_code = 0;
+
+	int fail(int code, const std::string &m) {
+		if (!err_code) {
+			err_code = code;
+			err = m;
+		}
+		return code;
+	}
+	int cuda(cudaError_t e, const char *what) {
+		if (e == cudaSuccess)
+			return 0;
+		return fail(DNG_ECUDA, std::string(what) + ": " +
+		    cudaGetErrorString(e));
+	}
+};
+
+#define CK(s, call) do { if ((s)->cuda((call), #call)) return (s)->err_code; } while (0)
+
+namespace {
+
+cudaEvent_t get_event(dng_scan *s)
+{
+	if (!s->ev_pool.empty()) {
+		cudaEvent_t e = s->ev_pool.back();
+		s->ev_pool.pop_back();
+		return e;
+	}
+	cudaEvent_t e;
+	cudaEventCreate(&e);
+	return e;
+}
+
+/* launch the scan kernel over data[start, nbytes) */
+int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
+    unsigned long long nbytes, bool final)
+{
+	if (nbytes <= start)
+		return 0;
+	ScanArgs a;
+	a.data = data;
+	a.start = start;
+	a.nbytes = nbytes;
+	a.plan = s->d_plan;
+	a.counters = s->d_counters;
+	a.tab = s->tab;
+	a.ntiles = (u32)((nbytes + DNG_TILE - 1) / DNG_TILE);
+	a.final = final ? 1 : 0;
+	u32 grid = std::min<u32>(a.ntiles, (u32)s->sm_count * DNG_CTAS_PER_SM);
+	cudaEvent_t e0 = get_event(s), e1 = get_event(s);
+	cudaEventRecord(e0, s->stream);
+	scan_kernel<<<grid, DNG_NT, SMEM_TOTAL, s->stream>>>(a);
+	cudaEventRecord(e1, s->stream);
+	s->ev_pairs.emplace_back(e0, e1);
+	s->launches++;
+	s->kernel_bytes += nbytes - start;
+	return s->cuda(cudaGetLastError(), "scan_kernel launch");
+}
+
+void drain_events(dng_scan *s)
+{
+	for (auto &p : s->ev_pairs) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess)
+			s->kernel_ms += ms;
+		s->ev_pool.push_back(p.first);
+		s->ev_pool.push_back(p.second);
+	}
+	s->ev_pairs.clear();
+}
+
+/*
+ * One piece of host input (<= ring_cap bytes) whose bytes up to `upto`
+ * (exclusive; ends just after a newline) are complete lines.  The previous
+ * carry is prepended on the device; bytes [upto, len) become the new carry.
+ */
+int feed_piece(dng_scan *s, const u8 *buf, size_t len, size_t upto, bool pinned)
+{
+	size_t slot = s->next_slot;
+	s->next_slot = (slot + 1) % RING_SLOTS;
+	if (s->slot_used[slot])
+		CK(s, cudaEventSynchronize(s->ev_free[slot]));
+	const u8 *src = buf;
+	if (!pinned) {
+		memcpy(s->h_stage[slot], buf, len);
+		src = s->h_stage[slot];
+	}
+	u8 *dst = s->d_ring[slot] + CARRY_ROOM;
+	CK(s, cudaMemcpyAsync(dst, src, len, cudaMemcpyHostToDevice,
+	    s->copy_stream));
+	CK(s, cudaEventRecord(s->ev_ready[slot], s->copy_stream));
+	CK(s, cudaStreamWaitEvent(s->stream, s->ev_ready[slot], 0));
+	if (upto > 0) {
+		u8 *begin = dst - s->carry_len;
+		if (s->carry_len)
+			CK(s, cudaMemcpyAsync(begin, s->d_carry, s->carry_len,
+			    cudaMemcpyDeviceToDevice, s->stream));
+		u8 *base = (u8 *)((uintptr_t)begin & ~(uintptr_t)15);
+		if (launch_scan(s, base, (unsigned long long)(begin - base),
+		    (unsigned long long)(dst + upto - base), false))
+			return s->err_code;
+		s->carry_len = 0;
+	}
+	if (len > upto) {
+		size_t tail = len - upto;
+		if (s->carry_len + tail > DNG_MAXREC)
+			return s->fail(DNG_ELIMIT, "input line longer than 16 MiB");
+		CK(s, cudaMemcpyAsync(s->d_carry + s->carry_len, dst + upto, tail,
+		    cudaMemcpyDeviceToDevice, s->stream));
+		s->carry_len += tail;
+	}
+	CK(s, cudaEventRecord(s->ev_free[slot], s->stream));
+	s->slot_used[slot] = true;
+	return 0;
+}
+
+int feed_host(dng_scan *s, const void *vbuf, size_t len, bool pinned)
+{
+	if (s->err_code)
+		return s->err_code;
+	if (s->finished)
+		return s->fail(DNG_EINVAL, "scan already finished");
+	const u8 *buf = (const u8 *)vbuf;
+	s->bytes_fed += len;
+	while (len > 0) {
+		size_t n = std::min(len, s->ring_cap);
+		/* complete lines end at the last '\n' of the piece */
+		const void *nl = memrchr(buf, '\n', n);
+		size_t upto = nl ? (size_t)((const u8 *)nl - buf) + 1 : 0;
+		int rc = feed_piece(s, buf, n, upto, pinned);
+		if (rc)
+			return rc;
+		buf += n;
+		len -= n;
+	}
+	return 0;
+}
+
+} /* namespace */
+
+extern "C" {
+
+const char *dng_version(void)
+{
+	return "dragnet-b200 0.1 (sm_100a)";
+}
+
+int dng_plan_create(const char *plan_json, dng_plan **out, char *err,
+    size_t errlen)
+{
+	if (!plan_json || !out) {
+		set_err(err, errlen, "null argument");
+		return DNG_EINVAL;
+	}
+	dng_plan *p = new dng_plan();
+	int rc = dng_plan_compile(plan_json, p, err, errlen);
+	if (rc) {
+		delete p;
+		return rc;
+	}
+	*out = p;
+	return DNG_OK;
+}
+
+void dng_plan_destroy(dng_plan *plan)
+{
+	delete plan;
+}
+
+int dng_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess)
+		return 0;
+	return n;
+}
+
+int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
+    size_t errlen)
+{
+	if (!plan || !out) {
+		set_err(err, errlen, "null argument");
+		return DNG_EINVAL;
+	}
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+		set_err(err, errlen, "no usable CUDA device (%s); "
+		    "libdragnet_gpu has no CPU fallback", e != cudaSuccess ?
+		    cudaGetErrorString(e) : "device index out of range");
+		return DNG_ENODEV;
+	}
+	dng_scan *s = new dng_scan();
+	s->plan = *plan;
+	s->device = device;
+	int rc = 0;
+	do {
+		if ((rc = s->cuda(cudaSetDevice(device), "cudaSetDevice")))
+			break;
+		cudaDeviceProp prop;
+		if ((rc = s->cuda(cudaGetDeviceProperties(&prop, device),
+		    "cudaGetDeviceProperties")))
+			break;
+		s->sm_count = prop.multiProcessorCount;
+		if ((rc = s->cuda(cudaFuncSetAttribute(scan_kernel,
+		    cudaFuncAttributeMaxDynamicSharedMemorySize,
+		    (int)SMEM_TOTAL), "cudaFuncSetAttribute")))
+			break;
+		if ((rc = s->cuda(cudaStreamCreateWithFlags(&s->stream,
+		    cudaStreamNonBlocking), "cudaStreamCreate")))
+			break;
+		if ((rc = s->cuda(cudaStreamCreateWithFlags(&s->copy_stream,
+		    cudaStreamNonBlocking), "cudaStreamCreate")))
+			break;
+		if ((rc = s->cuda(cudaMalloc(&s->d_plan, sizeof (DevPlan)),
+		    "cudaMalloc plan")))
+			break;
+		if ((rc = s->cuda(cudaMemcpy(s->d_plan, &plan->dev,
+		    sizeof (DevPlan), cudaMemcpyHostToDevice), "plan upload")))
+			break;
+		size_t cap = env_size("DNG_TABLE_CAP", (size_t)1 << 20);
+		size_t c2 = 1024;
+		while (c2 < cap)
+			c2 <<= 1;
+		s->table_cap = c2;
+		size_t arena = env_size("DNG_ARENA_BYTES", (size_t)64 << 20);
+		if ((rc = s->cuda(cudaMalloc(&s->tab.entries,
+		    c2 * sizeof (GEntry)), "cudaMalloc table")))
+			break;
+		if ((rc = s->cuda(cudaMalloc(&s->tab.arena, arena),
+		    "cudaMalloc arena")))
+			break;
+		if ((rc = s->cuda(cudaMalloc(&s->tab.misc, 16 * sizeof (u32)),
+		    "cudaMalloc misc")))
+			break;
+		s->tab.mask = (u32)(c2 - 1);
+		s->tab.arena_cap = (u32)arena;
+		cudaMemset(s->tab.entries, 0, c2 * sizeof (GEntry));
+		cudaMemset(s->tab.misc, 0, 16 * sizeof (u32));
+		if ((rc = s->cuda(cudaMalloc(&s->d_counters,
+		    NCTR * sizeof (unsigned long long)), "cudaMalloc counters")))
+			break;
+		cudaMemset(s->d_counters, 0, NCTR * sizeof (unsigned long long));
+		if ((rc = s->cuda(cudaMalloc(&s->d_nl,
+		    2 * sizeof (unsigned long long)), "cudaMalloc nl")))
+			break;
+		if ((rc = s->cuda(cudaMalloc(&s->d_carry, CARRY_ROOM + 64),
+		    "cudaMalloc carry")))
+			break;
+		s->ring_cap = env_size("DNG_RING_BYTES", (size_t)64 << 20);
+		rc = s->cuda(cudaDeviceSynchronize(), "init");
+	} while (0);
+	if (rc) {
+		set_err(err, errlen, "%s", s->err.c_str());
+		dng_scan_destroy(s);
+		return rc;
+	}
+	*out = s;
+	set_err(err, errlen, "");
+	return DNG_OK;
+}
+
+static int ensure_ring(dng_scan *s, bool need_stage)
+{
+	for (size_t i = 0; i < RING_SLOTS; i++) {
+		if (!s->d_ring[i]) {
+			CK(s, cudaMalloc(&s->d_ring[i], CARRY_ROOM +
+			    s->ring_cap + 64));
+			CK(s, cudaEventCreateWithFlags(&s->ev_ready[i],
+			    cudaEventDisableTiming));
+			CK(s, cudaEventCreateWithFlags(&s->ev_free[i],
+			    cudaEventDisableTiming));
+		}
+		if (need_stage && !s->h_stage[i])
+			CK(s, cudaMallocHost(&s->h_stage[i], s->ring_cap));
+	}
+	return 0;
+}
+
+int dng_scan_feed(dng_scan *s, const void *buf, size_t len)
+{
+	if (!s || (!buf && len))
+		return DNG_EINVAL;
+	cudaSetDevice(s->device);
+	if (ensure_ring(s, true))
+		return s->err_code;
+	return feed_host(s, buf, len, false);
+}
+
+int dng_scan_feed_pinned(dng_scan *s, const void *buf, size_t len)
+{
+	if (!s || (!buf && len))
+		return DNG_EINVAL;
+	cudaSetDevice(s->device);
+	if (ensure_ring(s, false))
+		return s->err_code;
+	return feed_host(s, buf, len, true);
+}
+
+int dng_scan_feed_file(dng_scan *s, const char *path)
+{
+	if (!s || !path)
+		return DNG_EINVAL;
+	cudaSetDevice(s->device);
+	if (ensure_ring(s, true))
+		return s->err_code;
+	int fd = open(path, O_RDONLY);
+	if (fd < 0)
+		return s->fail(DNG_EIO, std::string("open ") + path + ": " +
+		    strerror(errno));
+	/* read(2) straight into pinned buffers and DMA from them; a buffer is
+	 * reused only after the copy issued from it has landed */
+	size_t cap = std::min(s->ring_cap, (size_t)16 << 20);
+	u8 *bufs[2] = { nullptr, nullptr };
+	cudaEvent_t done[2] = { nullptr, nullptr };
+	bool inflight[2] = { false, false };
+	int rc = 0;
+	for (int i = 0; i < 2 && !rc; i++) {
+		rc = s->cuda(cudaMallocHost(&bufs[i], cap), "cudaMallocHost");
+		if (!rc)
+			rc = s->cuda(cudaEventCreateWithFlags(&done[i],
+			    cudaEventDisableTiming), "cudaEventCreate");
+	}
+	int which = 0;
+	while (!rc) {
+		if (inflight[which]) {
+			rc = s->cuda(cudaEventSynchronize(done[which]),
+			    "copy sync");
+			if (rc)
+				break;
+		}
+		ssize_t n = read(fd, bufs[which], cap);
+		if (n < 0) {
+			rc = s->fail(DNG_EIO, std::string("read ") + path + ": " +
+			    strerror(errno));
+			break;
+		}
+		if (n == 0)
+			break;
+		rc = feed_host(s, bufs[which], (size_t)n, true);
+		if (!rc)
+			rc = s->cuda(cudaEventRecord(done[which], s->copy_stream),
+			    "cudaEventRecord");
+		inflight[which] = true;
+		which ^= 1;
+	}
+	close(fd);
+	cudaStreamSynchronize(s->copy_stream);
+	for (int i = 0; i < 2; i++) {
+		if (bufs[i])
+			cudaFreeHost(bufs[i]);
+		if (done[i])
+			cudaEventDestroy(done[i]);
+	}
+	return rc;
+}
+
+int dng_scan_feed_device(dng_scan *s, const void *devbuf, size_t len)
+{
+	if (!s || (!devbuf && len))
+		return DNG_EINVAL;
+	if (s->err_code)
+		return s->err_code;
+	if (s->finished)
+		return s->fail(DNG_EINVAL, "scan already finished");
+	if ((uintptr_t)devbuf & 15)
+		return s->fail(DNG_EINVAL, "device buffer must be 16-byte "
+		    "aligned");
+	if (len == 0)
+		return 0;
+	cudaSetDevice(s->device);
+	const u8 *d = (const u8 *)devbuf;
+	s->bytes_fed += len;
+	/* locate the first and last newline (windows first, then all) */
+	unsigned long long init[2] = { ~0ull, 0 }, got[2];
+	const unsigned long long W = 1 << 20;
+	for (int attempt = 0; attempt < 2; attempt++) {
+		CK(s, cudaMemcpyAsync(s->d_nl, init, sizeof (init),
+		    cudaMemcpyHostToDevice, s->stream));
+		if (attempt == 0) {
+			find_nl_kernel<<<64, 256, 0, s->stream>>>(d, 0,
+			    std::min<unsigned long long>(len, W), s->d_nl,
+			    s->d_nl + 1);
+			if (len > W)
+				find_nl_kernel<<<64, 256, 0, s->stream>>>(d,
+				    len - W, len, s->d_nl, s->d_nl + 1);
+		} else {
+			find_nl_kernel<<<1024, 256, 0, s->stream>>>(d, 0, len,
+			    s->d_nl, s->d_nl + 1);
+		}
+		CK(s, cudaMemcpyAsync(got, s->d_nl, sizeof (got),
+		    cudaMemcpyDeviceToHost, s->stream));
+		CK(s, cudaStreamSynchronize(s->stream));
+		/* with windows: `first` is only trustworthy if it fell in the
+		 * head window, `last` if it fell in the tail window */
+		bool first_ok = got[0] != ~0ull && (len <= W || got[0] < W);
+		bool last_ok = got[1] != 0 && (len <= W || got[1] > len - W);
+		if ((first_ok && last_ok) || attempt == 1 || len <= W)
+			break;
+	}
+	if (got[0] == ~0ull) {
+		/* no newline at all: the whole chunk extends the carry */
+		if (s->carry_len + len > DNG_MAXREC)
+			return s->fail(DNG_ELIMIT, "input line longer than 16 MiB");
+		CK(s, cudaMemcpyAsync(s->d_carry + s->carry_len, d, len,
+		    cudaMemcpyDeviceToDevice, s->stream));
+		s->carry_len += len;
+		return 0;
+	}
+	unsigned long long first = got[0], last = got[1];
+	unsigned long long start = 0;
+	if (s->carry_len) {
+		/* finish the carried line in a side buffer */
+		size_t head = (size_t)first + 1;
+		if (s->carry_len + head > DNG_MAXREC)
+			return s->fail(DNG_ELIMIT, "input line longer than 16 MiB");
+		if (!s->d_side)
+			CK(s, cudaMalloc(&s->d_side, CARRY_ROOM + 64));
+		CK(s, cudaMemcpyAsync(s->d_side, s->d_carry, s->carry_len,
+		    cudaMemcpyDeviceToDevice, s->stream));
+		CK(s, cudaMemcpyAsync(s->d_side + s->carry_len, d, head,
+		    cudaMemcpyDeviceToDevice, s->stream));
+		if (launch_scan(s, s->d_side, 0, s->carry_len + head, false))
+			return s->err_code;
+		s->carry_len = 0;
+		start = head;
+	}
+	if (launch_scan(s, d, start, last, false))
+		return s->err_code;
+	if (last < len) {
+		size_t tail = len - (size_t)last;
+		if (tail > DNG_MAXREC)
+			return s->fail(DNG_ELIMIT, "input line longer than 16 MiB");
+		CK(s, cudaMemcpyAsync(s->d_carry, d + last, tail,
+		    cudaMemcpyDeviceToDevice, s->stream));
+		s->carry_len = tail;
+	}
+	return 0;
+}
+
+int dng_scan_sync(dng_scan *s)
+{
+	if (!s)
+		return DNG_EINVAL;
+	cudaSetDevice(s->device);
+	CK(s, cudaStreamSynchronize(s->copy_stream));
+	CK(s, cudaStreamSynchronize(s->stream));
+	drain_events(s);
+	return s->err_code;
+}
+
+static int flush_tail(dng_scan *s)
+{
+	if (s->finished)
+		return 0;
+	s->finished = true;
+	if (s->carry_len) {
+		/* lstream emits the final unterminated line */
+		if (launch_scan(s, s->d_carry, 0, s->carry_len, true))
+			return s->err_code;
+		s->carry_len = 0;
+	}
+	return 0;
+}
+
+int dng_scan_counters(dng_scan *s, dng_counters *out)
+{
+	if (!s || !out)
+		return DNG_EINVAL;
+	cudaSetDevice(s->device);
+	if (dng_scan_sync(s))
+		return s->err_code;
+	unsigned long long c[NCTR];
+	CK(s, cudaMemcpy(c, s->d_counters, sizeof (c), cudaMemcpyDeviceToHost));
+	memset(out, 0, sizeof (*out));
+	out->lines = c[CTR_LINES];
+	out->invalid_json = c[CTR_INVALID_JSON];
+	out->invalid_point = c[CTR_INVALID_POINT];
+	out->ds_filtered = c[CTR_DS_FILTERED];
+	out->ds_failedeval = c[CTR_DS_FAILED];
+	out->user_filtered = c[CTR_USER_FILTERED];
+	out->user_failedeval = c[CTR_USER_FAILED];
+	out->synth_undef = c[CTR_SYNTH_UNDEF];
+	out->synth_baddate = c[CTR_SYNTH_BADDATE];
+	out->time_filtered = c[CTR_TIME_FILTERED];
+	out->time_failedeval = c[CTR_TIME_FAILED];
+	out->aggr_ninputs = c[CTR_AGGR];
+	out->slowpath_records = c[CTR_SLOW];
+	out->unsupported = c[CTR_UNSUPPORTED];
+	out->long_records = c[CTR_LONG];
+	out->bytes = s->bytes_fed;
+	uint64_t n = out->lines - out->invalid_json - out->invalid_point;
+	const DevPlan &P = s->plan.dev;
+	if (P.ds_entry >= 0) {
+		out->ds_ninputs = n;
+		n -= out->ds_filtered + out->ds_failedeval;
+	}
+	if (P.user_entry >= 0) {
+		out->user_ninputs = n;
+		n -= out->user_filtered + out->user_failedeval;
+	}
+	if (P.nsyn) {
+		out->synth_ninputs = n;
+		n -= out->synth_undef + out->synth_baddate;
+	}
+	if (P.time_entry >= 0)
+		out->time_ninputs = n;
+	return DNG_OK;
+}
+
+int dng_scan_finish(dng_scan *s, dng_result **out)
+{
+	if (!s || !out)
+		return DNG_EINVAL;
+	if (s->err_code)
+		return s->err_code;
+	cudaSetDevice(s->device);
+	if (flush_tail(s))
+		return s->err_code;
+	if (dng_scan_sync(s))
+		return s->err_code;
+	u32 misc[4];
+	CK(s, cudaMemcpy(misc, s->tab.misc, sizeof (misc),
+	    cudaMemcpyDeviceToHost));
+	if (misc[2] & ST_TABLE_FULL)
+		return s->fail(DNG_ELIMIT, "too many distinct tuples for the "
+		    "device table (raise DNG_TABLE_CAP)");
+	if (misc[2] & ST_ARENA_FULL)
+		return s->fail(DNG_ELIMIT, "group-key arena exhausted (raise "
+		    "DNG_ARENA_BYTES)");
+	dng_counters c;
+	if (dng_scan_counters(s, &c))
+		return s->err_code;
+	if (c.unsupported)
+		return s->fail(DNG_EUNSUPPORTED, "input contains records the "
+		    "device path cannot decide yet (" +
+		    std::to_string(c.unsupported) + "): nesting deeper than 64, "
+		    "a group key longer than 512 bytes, a line >= 16 MiB, or "
+		    "an array where an index/length lookup is needed");
+	u32 n = misc[1];
+	dng_result *r = new dng_result();
+	r->init_from_plan(&s->plan);
+	uint64_t total = 0;
+	if (n) {
+		OutEntry *d_out = nullptr;
+		u32 *d_n = nullptr;
+		CK(s, cudaMalloc(&d_out, (size_t)n * sizeof (OutEntry)));
+		CK(s, cudaMalloc(&d_n, sizeof (u32)));
+		CK(s, cudaMemsetAsync(d_n, 0, sizeof (u32), s->stream));
+		compact_kernel<<<256, 256, 0, s->stream>>>(s->tab.entries,
+		    s->tab.mask + 1, d_out, d_n);
+		std::vector<OutEntry> ents(n);
+		std::vector<u8> arena(misc[0]);
+		CK(s, cudaMemcpyAsync(ents.data(), d_out,
+		    (size_t)n * sizeof (OutEntry), cudaMemcpyDeviceToHost,
+		    s->stream));
+		if (misc[0])
+			CK(s, cudaMemcpyAsync(arena.data(), s->tab.arena, misc[0],
+			    cudaMemcpyDeviceToHost, s->stream));
+		CK(s, cudaStreamSynchronize(s->stream));
+		cudaFree(d_out);
+		cudaFree(d_n);
+		r->keys.reserve(n);
+		r->values.reserve(n);
+		for (u32 i = 0; i < n; i++) {
+			r->keys.emplace_back((const char *)arena.data() +
+			    ents[i].koff, ents[i].klen);
+			r->values.push_back(ents[i].count);
+			total += ents[i].count;
+		}
+	}
+	r->finalize(total);
+	*out = r;
+	return DNG_OK;
+}
+
+const char *dng_scan_error(const dng_scan *s)
+{
+	return s ? s->err.c_str() : "null scan";
+}
+
+int dng_scan_kernel_stats(dng_scan *s, double *kernel_ms, uint64_t *launches,
+    uint64_t *kernel_bytes)
+{
+	if (!s)
+		return DNG_EINVAL;
+	cudaSetDevice(s->device);
+	if (dng_scan_sync(s))
+		return s->err_code;
+	if (kernel_ms)
+		*kernel_ms = s->kernel_ms;
+	if (launches)
+		*launches = s->launches;
+	if (kernel_bytes)
+		*kernel_bytes = s->kernel_bytes;
+	return DNG_OK;
+}
+
+void dng_scan_destroy(dng_scan *s)
+{
+	if (!s)
+		return;
+	cudaSetDevice(s->device);
+	cudaDeviceSynchronize();
+	drain_events(s);
+	for (auto e : s->ev_pool)
+		cudaEventDestroy(e);
+	for (size_t i = 0; i < RING_SLOTS; i++) {
+		if (s->d_ring[i]) {
+			cudaFree(s->d_ring[i]);
+			cudaEventDestroy(s->ev_ready[i]);
+			cudaEventDestroy(s->ev_free[i]);
+		}
+		if (s->h_stage[i])
+			cudaFreeHost(s->h_stage[i]);
+	}
+	cudaFree(s->d_plan);
+	cudaFree(s->tab.entries);
+	cudaFree(s->tab.arena);
+	cudaFree(s->tab.misc);
+	cudaFree(s->d_counters);
+	cudaFree(s->d_nl);
+	cudaFree(s->d_carry);
+	cudaFree(s->d_side);
+	if (s->stream)
+		cudaStreamDestroy(s->stream);
+	if (s->copy_stream)
+		cudaStreamDestroy(s->copy_stream);
+	delete s;
+}
+
+void *dng_pinned_alloc(size_t len)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, len) != cudaSuccess)
+		return nullptr;
+	return p;
+}
+
+void dng_pinned_free(void *p)
+{
+	if (p)
+		cudaFreeHost(p);
+}
+
+/* ---- results ------------------------------------------------------------ */
+
+size_t dng_result_count(const dng_result *r)
+{
+	return r ? r->keys.size() : 0;
+}
+
+size_t dng_result_ncols(const dng_result *r)
+{
+	return r ? (size_t)r->ncols : 0;
+}
+
+int dng_result_get(const dng_result *r, size_t i, const char **strs,
+    size_t *strlens, uint8_t *is_number, double *numvals, uint64_t *value)
+{
+	if (!r || i >= r->keys.size())
+		return DNG_EINVAL;
+	for (int j = 0; j < r->ncols; j++) {
+		const dng_result::Cell &c = r->cells[i * r->ncols + j];
+		if (is_number)
+			is_number[j] = c.is_number;
+		if (numvals)
+			numvals[j] = c.num;
+		if (strs)
+			strs[j] = c.is_number ? nullptr :
+			    r->keys[i].data() + c.off;
+		if (strlens)
+			strlens[j] = c.is_number ? 0 : c.len;
+	}
+	if (value)
+		*value = r->values[i];
+	return DNG_OK;
+}
+
+void dng_result_destroy(dng_result *r)
+{
+	delete r;
+}
+
+/* ---- synthetic input ------------------------------------------------------ */
+
+void dng_gen_defaults(dng_gen_params *p)
+{
+	p->seed = 0xD5A60000ull;
+	p->total_records = 1000;
+	p->time_min_ms = 1401570000000ll;	/* 2014-05-31T21:00:00Z */
+	p->time_max_ms = 1401580799000ll;	/* 2014-05-31T23:59:59Z */
+	p->string_latency = 0;
+}
+
+int dng_gen_host(const dng_gen_params *p, uint64_t first, uint64_t count,
+    void *buf, size_t cap, size_t *len)
+{
+	if (!p || !buf || !len)
+		return DNG_EINVAL;
+	char *o = (char *)buf;
+	size_t n = 0;
+	char tmp[GEN_MAXREC];
+	for (uint64_t j = first; j < first + count; j++) {
+		int k = gen_record(*p, j, tmp);
+		if (n + (size_t)k > cap)
+			return DNG_ELIMIT;
+		memcpy(o + n, tmp, (size_t)k);
+		n += (size_t)k;
+	}
+	*len = n;
+	return DNG_OK;
+}
+
+} /* extern "C" */
+
+namespace {
+
+__global__ void gen_len_kernel(dng_gen_params p, uint64_t first, uint64_t count,
+    unsigned long long *block_sums, u32 *lens)
+{
+	__shared__ u32 red[256 / 32];
+	uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	char tmp[GEN_MAXREC];
+	u32 k = 0;
+	if (j < count) {
+		k = (u32)gen_record(p, first + j, tmp);
+		lens[j] = k;
+	}
+	u32 v = k;
+	for (int d = 16; d > 0; d >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, d);
+	if ((threadIdx.x & 31) == 0)
+		red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		u32 t = 0;
+		for (int i = 0; i < 256 / 32; i++)
+			t += red[i];
+		block_sums[blockIdx.x] = t;
+	}
+}
+
+__global__ void gen_write_kernel(dng_gen_params p, uint64_t first,
+    uint64_t count, const unsigned long long *block_offs, const u32 *lens,
+    char *out)
+{
+	__shared__ u32 soff[256];
+	uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	u32 k = j < count ? lens[j] : 0;
+	soff[threadIdx.x] = k;
+	__syncthreads();
+	/* exclusive scan within the block (serial by thread 0: 256 adds) */
+	if (threadIdx.x == 0) {
+		u32 acc = 0;
+		for (int i = 0; i < 256; i++) {
+			u32 t = soff[i];
+			soff[i] = acc;
+			acc += t;
+		}
+	}
+	__syncthreads();
+	if (j < count) {
+		char tmp[GEN_MAXREC];
+		int n = gen_record(p, first + j, tmp);
+		char *dst = out + block_offs[blockIdx.x] + soff[threadIdx.x];
+		for (int i = 0; i < n; i++)
+			dst[i] = tmp[i];
+	}
+}
+
+} /* namespace */
+
+extern "C" int dng_gen_device(const dng_gen_params *p, int device,
+    uint64_t first, uint64_t count, void *devbuf, size_t cap, size_t *len)
+{
+	if (!p || !devbuf || !len)
+		return DNG_EINVAL;
+	if (cudaSetDevice(device) != cudaSuccess)
+		return DNG_ENODEV;
+	if (count == 0) {
+		*len = 0;
+		return DNG_OK;
+	}
+	u32 nblocks = (u32)((count + 255) / 256);
+	unsigned long long *d_sums = nullptr;
+	u32 *d_lens = nullptr;
+	int rc = DNG_OK;
+	if (cudaMalloc(&d_sums, (size_t)nblocks * 8) != cudaSuccess ||
+	    cudaMalloc(&d_lens, (size_t)count * 4) != cudaSuccess) {
+		cudaFree(d_sums);
+		cudaFree(d_lens);
+		return DNG_ENOMEM;
+	}
+	gen_len_kernel<<<nblocks, 256>>>(*p, first, count, d_sums, d_lens);
+	std::vector<unsigned long long> sums(nblocks);
+	if (cudaMemcpy(sums.data(), d_sums, (size_t)nblocks * 8,
+	    cudaMemcpyDeviceToHost) != cudaSuccess)
+		rc = DNG_ECUDA;
+	unsigned long long acc = 0;
+	for (u32 i = 0; i < nblocks; i++) {
+		unsigned long long t = sums[i];
+		sums[i] = acc;
+		acc += t;
+	}
+	if (!rc && acc > cap)
+		rc = DNG_ELIMIT;
+	if (!rc) {
+		cudaMemcpy(d_sums, sums.data(), (size_t)nblocks * 8,
+		    cudaMemcpyHostToDevice);
+		gen_write_kernel<<<nblocks, 256>>>(*p, first, count, d_sums,
+		    d_lens, (char *)devbuf);
+		if (cudaDeviceSynchronize() != cudaSuccess)
+			rc = DNG_ECUDA;
+		*len = (size_t)acc;
+	}
+	cudaFree(d_sums);
+	cudaFree(d_lens);
+	return rc;
+}

@@ -34,7 +34,7 @@ DNG_HD int64_t days_from_civil(int64_t y, int m, int d)
 }
 
 /* returns true and *ms on success; false for NaN */
-DNG_HD bool dng_date_parse(const uint8_t *p, int n, int64_t *ms)
+DNG_HDN bool dng_date_parse(const uint8_t *p, int n, int64_t *ms)
 {
 	int i = 0;
 	int64_t y = 0;

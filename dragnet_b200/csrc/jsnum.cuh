@@ -23,9 +23,11 @@
 
 #ifdef __CUDACC__
 #define DNG_HD __host__ __device__ __forceinline__
+#define DNG_HDI __host__ __device__ inline
 #define DNG_HDN __host__ __device__ __noinline__ inline
 #else
 #define DNG_HD inline
+#define DNG_HDI inline
 #define DNG_HDN inline
 #endif
 
@@ -39,7 +41,7 @@ struct Big {
 	int overflow;
 };
 
-DNG_HD void big_set(Big &b, uint64_t v)
+DNG_HDN void big_set(Big &b, uint64_t v)
 {
 	b.n = 0;
 	b.overflow = 0;
@@ -50,7 +52,7 @@ DNG_HD void big_set(Big &b, uint64_t v)
 	}
 }
 
-DNG_HD void big_mul_small(Big &b, uint32_t m, uint32_t add)
+DNG_HDN void big_mul_small(Big &b, uint32_t m, uint32_t add)
 {
 	uint64_t carry = add;
 	for (int i = 0; i < b.n; i++) {
@@ -66,7 +68,7 @@ DNG_HD void big_mul_small(Big &b, uint32_t m, uint32_t add)
 	}
 }
 
-DNG_HD void big_mul_pow10(Big &b, int e)
+DNG_HDN void big_mul_pow10(Big &b, int e)
 {
 	while (e >= 9) {
 		big_mul_small(b, 1000000000u, 0);
@@ -80,7 +82,7 @@ DNG_HD void big_mul_pow10(Big &b, int e)
 }
 
 /* b /= d; returns remainder */
-DNG_HD uint32_t big_div_small(Big &b, uint32_t d)
+DNG_HDN uint32_t big_div_small(Big &b, uint32_t d)
 {
 	uint64_t rem = 0;
 	for (int i = b.n - 1; i >= 0; i--) {
@@ -93,7 +95,7 @@ DNG_HD uint32_t big_div_small(Big &b, uint32_t d)
 	return (uint32_t)rem;
 }
 
-DNG_HD void big_shl(Big &b, int k)
+DNG_HDN void big_shl(Big &b, int k)
 {
 	if (b.n == 0 || k == 0)
 		return;
@@ -119,7 +121,7 @@ DNG_HD void big_shl(Big &b, int k)
 		b.n--;
 }
 
-DNG_HD int big_bitlen(const Big &b)
+DNG_HDN int big_bitlen(const Big &b)
 {
 	if (b.n == 0)
 		return 0;
@@ -132,7 +134,7 @@ DNG_HD int big_bitlen(const Big &b)
 	return (b.n - 1) * 32 + l;
 }
 
-DNG_HD int big_cmp(const Big &a, const Big &b)
+DNG_HDN int big_cmp(const Big &a, const Big &b)
 {
 	if (a.n != b.n)
 		return a.n < b.n ? -1 : 1;
@@ -144,7 +146,7 @@ DNG_HD int big_cmp(const Big &a, const Big &b)
 }
 
 /* a -= b (requires a >= b) */
-DNG_HD void big_sub(Big &a, const Big &b)
+DNG_HDN void big_sub(Big &a, const Big &b)
 {
 	int64_t borrow = 0;
 	for (int i = 0; i < a.n; i++) {
@@ -157,7 +159,7 @@ DNG_HD void big_sub(Big &a, const Big &b)
 }
 
 /* cmp(a + b, c) without materialising the sum beyond a temp */
-DNG_HD int big_cmp_sum(const Big &a, const Big &b, const Big &c, Big &tmp)
+DNG_HDN int big_cmp_sum(const Big &a, const Big &b, const Big &c, Big &tmp)
 {
 	int n = a.n > b.n ? a.n : b.n;
 	uint64_t carry = 0;
@@ -191,7 +193,7 @@ DNG_HD uint64_t double_to_bits(double d)
  * Round (mant64 * 2^e2), mant64 normalised (bit 63 set), plus a sticky bit
  * for discarded lower-order value, to the nearest binary64 (ties to even).
  */
-DNG_HD double round_to_double(uint64_t mant64, int e2, int sticky)
+DNG_HDN double round_to_double(uint64_t mant64, int e2, int sticky)
 {
 	int E = e2 + 63;
 	if (E > 1023)
@@ -364,7 +366,7 @@ DNG_HDN double dng_parse_decimal_slow(const uint8_t *p, int len)
 }
 
 /* decimal -> double; fast path for <= 19 digits and small exponents */
-DNG_HD double dng_parse_decimal(const uint8_t *p, int len)
+DNG_HDN double dng_parse_decimal(const uint8_t *p, int len)
 {
 	int i = 0, neg = 0;
 	if (i < len && (p[i] == '-' || p[i] == '+')) {
@@ -518,7 +520,7 @@ DNG_HDN void dng_shortest_digits(double v, char *digits, int *nd, int *n)
 }
 
 /* Number::toString(v) into out (>= 32 bytes); returns length */
-DNG_HD int dng_number_to_string(double v, char *out)
+DNG_HDN int dng_number_to_string(double v, char *out)
 {
 	int o = 0;
 	if (v != v) {
@@ -628,7 +630,7 @@ DNG_HD double dng_nan()
 }
 
 /* ToNumber(string): p[0..len) is the string's UTF-8 */
-DNG_HD double dng_string_to_number(const uint8_t *p, int len)
+DNG_HDN double dng_string_to_number(const uint8_t *p, int len)
 {
 	int a = 0, b = len, l;
 	while (a < b && (l = js_space_len(p + a, b - a)) > 0)

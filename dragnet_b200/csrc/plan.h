@@ -33,6 +33,8 @@ enum ValType : u8 {
 enum : u8 {
 	VF_ESCAPED = 1,		/* string contains a backslash escape */
 	VF_SIMPLEINT = 2,	/* number is [-]digits, <= 15 digits, not "-0" */
+	/* 4 = VF_BINARY (record.cuh): number held as a double */
+	VF_INLINE = 8,		/* number is the value's `off` field itself */
 };
 
 enum : int {

@@ -118,7 +118,7 @@ DNG_HD int decode_unit(const u8 *s, u32 n, u32 &i, u8 *out)
 }
 
 /* escaped JSON string body == target bytes? */
-DNG_HD bool str_eq_escaped(const u8 *s, u32 n, const u8 *t, u32 tn)
+DNG_HDN bool str_eq_escaped(const u8 *s, u32 n, const u8 *t, u32 tn)
 {
 	u32 i = 0, j = 0;
 	u8 tmp[4];
@@ -135,7 +135,7 @@ DNG_HD bool str_eq_escaped(const u8 *s, u32 n, const u8 *t, u32 tn)
 }
 
 /* decode an escaped body into out (cap bytes); returns length or -1 */
-DNG_HD int str_decode(const u8 *s, u32 n, u8 *out, u32 cap)
+DNG_HDN int str_decode(const u8 *s, u32 n, u8 *out, u32 cap)
 {
 	u32 i = 0, j = 0;
 	u8 tmp[4];
@@ -165,6 +165,10 @@ DNG_HD void parse_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R)
 	u32 set_mask = 0;
 	u32 flags = 0;
 	u32 c = 0;
+	/* array-valued contexts (jsprim.pluck indexes arrays through
+	 * hasOwnProperty: "0", "1", ... and "length") */
+	u64 arrbits = 0;		/* bit 0: current context is an array */
+	u32 arr_idx[MAX_LEVELS + 2];	/* next element index, per ctx depth */
 
 	for (;;) {
 		for (;;) {
@@ -275,6 +279,36 @@ DNG_HD void parse_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R)
 		case S_VALUE: {
 			u32 vstart = i;
 			u64 v;
+			if ((arrbits & 1) && depth == ctx_depth && ctx >= 0) {
+				/* element of an array context: its key is the
+				 * decimal index */
+				const Ctx &cx = P.ctx[ctx];
+				u32 lvl = cx.depth;
+				u32 idx = arr_idx[lvl]++;
+				char ib[12];
+				u32 il = 0;
+				do {
+					ib[il++] = (char)('0' + idx % 10);
+					idx /= 10;
+				} while (idx);
+				pend_term = -1;
+				pend_child = -1;
+				for (u32 ci = cx.cand_begin; ci < cx.cand_end;
+				    ci++) {
+					const Cand &cd = P.cand[ci];
+					if (cd.len != il)
+						continue;
+					const u8 *t = (const u8 *)P.pool + cd.off;
+					u32 x = 0;
+					while (x < il && t[x] == (u8)ib[il - 1 - x])
+						x++;
+					if (x == il) {
+						pend_term = cd.term_slot;
+						pend_child = cd.child_ctx;
+						break;
+					}
+				}
+			}
 			if (c == '"') {
 				i++;
 				u32 esc = 0;
@@ -323,22 +357,21 @@ DNG_HD void parse_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R)
 					    T_OBJ : T_ARR, vstart, 0, 0);
 					set_mask |= 1u << pend_term;
 				}
+				int enter = -1;
 				if (pend_child >= 0) {
 					set_mask &=
 					    ~P.ctx[pend_child].subtree_mask;
-					if (isobj) {
-						ctx = pend_child;
-						ctx_depth = depth + 1;
-					} else if (P.ctx[pend_child].arraylike) {
-						flags |= RF_UNSUPPORTED;
-					}
-				} else if (depth == 0) {
-					if (isobj) {
-						ctx = 0;
-						ctx_depth = 1;
-					} else if (P.nctx && P.ctx[0].arraylike) {
-						flags |= RF_UNSUPPORTED;
-					}
+					enter = pend_child;
+				} else if (depth == 0 && P.nctx) {
+					enter = 0;
+				}
+				if (enter >= 0 && (isobj ||
+				    P.ctx[enter].arraylike)) {
+					ctx = enter;
+					ctx_depth = depth + 1;
+					arrbits = (arrbits << 1) | (isobj ? 0 : 1);
+					if (!isobj)
+						arr_idx[P.ctx[enter].depth] = 0;
 				}
 				pend_term = -1;
 				pend_child = -1;
@@ -445,7 +478,26 @@ close:
 		if (((u32)(stk & 1)) != (u32)(c == '}'))
 			goto invalid;
 		if (depth == ctx_depth && ctx >= 0) {
-			ctx = P.ctx[ctx].parent;
+			const Ctx &cx = P.ctx[ctx];
+			if (arrbits & 1) {
+				/* arr.length */
+				for (u32 ci = cx.cand_begin; ci < cx.cand_end;
+				    ci++) {
+					const Cand &cd = P.cand[ci];
+					const u8 *t = (const u8 *)P.pool + cd.off;
+					if (cd.len == 6 && t[0] == 'l' &&
+					    t[1] == 'e' && t[2] == 'n' &&
+					    t[3] == 'g' && t[4] == 't' &&
+					    t[5] == 'h' && cd.term_slot >= 0) {
+						R.slots[cd.term_slot] = mkval(
+						    T_NUM, arr_idx[cx.depth], 0,
+						    VF_INLINE);
+						set_mask |= 1u << cd.term_slot;
+					}
+				}
+			}
+			arrbits >>= 1;
+			ctx = cx.parent;
 			ctx_depth--;
 		}
 		stk >>= 1;
@@ -470,7 +522,7 @@ struct V {
 	u64 pk;
 	double num;		/* when VF_BINARY */
 };
-enum : u32 { VF_BINARY = 4 };
+enum : u32 { VF_BINARY = 4 };	/* VF_INLINE (plan.h) = 8 */
 
 DNG_HD V get_src(const DevPlan &P, const RecState &R, Src s)
 {
@@ -520,6 +572,8 @@ DNG_HD double simple_int(const u8 *p, u32 n)
 
 DNG_HD double json_number(const u8 *rec, u64 pk)
 {
+	if (val_flags(pk) & VF_INLINE)
+		return (double)val_off(pk);
 	if (val_flags(pk) & VF_SIMPLEINT)
 		return simple_int(rec + val_off(pk), val_len(pk));
 	return dng_parse_decimal(rec + val_off(pk), (int)val_len(pk));
@@ -618,57 +672,68 @@ DNG_HDN void stringify_array(const u8 *rec, u32 off, u8 *out, u32 &o, u32 cap,
 /*
  * ToString(v) appended to out at o.  Used for discrete group keys
  * (String(value) as a JS property key) and Date.parse arguments.
+ * Out of line: everything but plain strings and plain integers.
  */
-DNG_HD void value_to_string(const u8 *rec, const V &v, u8 *out, u32 &o, u32 cap,
-    u32 &ovf, u32 &slow)
+DNG_HDN void value_to_string_slow(const u8 *rec, u64 pk, double num, u8 *out,
+    u32 &o, u32 cap, u32 &ovf)
 {
-	u32 t = val_type(v.pk), fl = val_flags(v.pk);
+	u32 t = val_type(pk), fl = val_flags(pk);
 	switch (t) {
 	case T_UNDEF: put_bytes(out, o, cap, "undefined", 9, ovf); break;
 	case T_NULL: put_bytes(out, o, cap, "null", 4, ovf); break;
 	case T_TRUE: put_bytes(out, o, cap, "true", 4, ovf); break;
 	case T_FALSE: put_bytes(out, o, cap, "false", 5, ovf); break;
 	case T_OBJ: put_bytes(out, o, cap, "[object Object]", 15, ovf); break;
-	case T_NUM:
-		if (fl & VF_SIMPLEINT) {
-			put_bytes(out, o, cap, (const char *)rec + val_off(v.pk),
-			    val_len(v.pk), ovf);
-		} else {
-			char nb[32];
-			double d = (fl & VF_BINARY) ? v.num :
-			    dng_parse_decimal(rec + val_off(v.pk),
-			    (int)val_len(v.pk));
-			int k = dng_number_to_string(d, nb);
-			put_bytes(out, o, cap, nb, k, ovf);
-			slow = 1;
-		}
+	case T_NUM: {
+		char nb[32];
+		double d = (fl & VF_BINARY) ? num :
+		    (fl & VF_INLINE) ? (double)val_off(pk) :
+		    dng_parse_decimal(rec + val_off(pk), (int)val_len(pk));
+		int k = dng_number_to_string(d, nb);
+		put_bytes(out, o, cap, nb, k, ovf);
 		break;
-	case T_STR:
-		if (!(fl & VF_ESCAPED)) {
-			put_bytes(out, o, cap, (const char *)rec + val_off(v.pk),
-			    val_len(v.pk), ovf);
-		} else {
-			int k = str_decode(rec + val_off(v.pk), val_len(v.pk),
-			    out + o, cap - o);
-			if (k < 0)
-				ovf = 1;
-			else
-				o += k;
-			slow = 1;
-		}
+	}
+	case T_STR: {
+		int k = str_decode(rec + val_off(pk), val_len(pk), out + o,
+		    cap - o);
+		if (k < 0)
+			ovf = 1;
+		else
+			o += k;
 		break;
+	}
 	case T_ARR:
-		stringify_array(rec, val_off(v.pk), out, o, cap, ovf);
-		slow = 1;
+		stringify_array(rec, val_off(pk), out, o, cap, ovf);
 		break;
 	}
 }
 
-/* ToNumber(v); scratch is used for escaped strings / arrays */
-DNG_HD double value_to_number(const u8 *rec, const V &v, u8 *scratch, u32 cap,
+DNG_HD void value_to_string(const u8 *rec, const V &v, u8 *out, u32 &o, u32 cap,
     u32 &ovf, u32 &slow)
 {
 	u32 t = val_type(v.pk), fl = val_flags(v.pk);
+	if ((t == T_STR && !(fl & VF_ESCAPED)) ||
+	    (t == T_NUM && (fl & VF_SIMPLEINT))) {
+		u32 n = val_len(v.pk), off = val_off(v.pk);
+		if (o + n > cap) {
+			ovf = 1;
+			return;
+		}
+		for (u32 k = 0; k < n; k++)
+			out[o + k] = rec[off + k];
+		o += n;
+		return;
+	}
+	if (t == T_STR || t == T_ARR || t == T_NUM)
+		slow = 1;
+	value_to_string_slow(rec, v.pk, v.num, out, o, cap, ovf);
+}
+
+/* ToNumber(v), out of line part; scratch is used for escaped strings/arrays */
+DNG_HDN double value_to_number_slow(const u8 *rec, u64 pk, u8 *scratch, u32 cap,
+    u32 &ovf)
+{
+	u32 t = val_type(pk), fl = val_flags(pk);
 	switch (t) {
 	case T_NULL:
 	case T_FALSE:
@@ -676,23 +741,37 @@ DNG_HD double value_to_number(const u8 *rec, const V &v, u8 *scratch, u32 cap,
 	case T_TRUE:
 		return 1.0;
 	case T_NUM:
-		if (fl & VF_BINARY)
-			return v.num;
-		return json_number(rec, v.pk);
+		if (fl & VF_INLINE)
+			return (double)val_off(pk);
+		return dng_parse_decimal(rec + val_off(pk), (int)val_len(pk));
 	case T_STR:
 		if (!(fl & VF_ESCAPED))
-			return dng_string_to_number(rec + val_off(v.pk),
-			    (int)val_len(v.pk));
+			return dng_string_to_number(rec + val_off(pk),
+			    (int)val_len(pk));
 		/* FALLTHROUGH */
 	case T_ARR: {
 		u32 o = 0;
-		value_to_string(rec, v, scratch, o, cap, ovf, slow);
-		slow = 1;
+		value_to_string_slow(rec, pk, 0.0, scratch, o, cap, ovf);
 		return dng_string_to_number(scratch, (int)o);
 	}
 	default:
 		return dng_nan();	/* undefined, objects */
 	}
+}
+
+DNG_HD double value_to_number(const u8 *rec, const V &v, u8 *scratch, u32 cap,
+    u32 &ovf, u32 &slow)
+{
+	u32 t = val_type(v.pk), fl = val_flags(v.pk);
+	if (t == T_NUM) {
+		if (fl & VF_BINARY)
+			return v.num;
+		if (fl & VF_SIMPLEINT)
+			return simple_int(rec + val_off(v.pk), val_len(v.pk));
+	}
+	if (t == T_STR || t == T_ARR)
+		slow = 1;
+	return value_to_number_slow(rec, v.pk, scratch, cap, ovf);
 }
 
 /* relational order of two UTF-8 strings by UTF-16 code units */
@@ -772,7 +851,7 @@ DNG_HD int eval_leaf(const u8 *rec, const DevPlan &P, const RecState &R,
 	}
 }
 
-DNG_HD int eval_program(const u8 *rec, const DevPlan &P, const RecState &R,
+DNG_HDN int eval_program(const u8 *rec, const DevPlan &P, const RecState &R,
     int entry, u8 *scratch, u32 &ovf, u32 &slow)
 {
 	int pc = entry;

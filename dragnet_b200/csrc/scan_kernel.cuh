@@ -1,0 +1,552 @@
+/*
+ * scan_kernel.cuh: the fused sm_100a scan kernel.
+ *
+ * One launch = one pass of dragnet's raw-scan pipeline over a byte range that
+ * is resident in HBM:
+ *
+ *   lstream line split      (lib/format-json.js:32-33)   newline index per tile
+ *   JSON.parse + adapter    (lib/format-json.js:34-46)   parse_record()
+ *   krill filters, dates,   (lib/stream-scan.js:56-86)   process_record()
+ *   time bounds
+ *   skinner aggregator      (lib/dragnet-impl.js:48-51)  shared-memory hash
+ *                                                        table -> global table
+ *
+ * Layout: persistent CTAs (2 per SM).  A CTA repeatedly takes a TILE of input,
+ * stages [tile - PRELAP, tile + TILE) into shared memory with one TMA bulk
+ * copy (cp.async.bulk + mbarrier), indexes the newlines in its tile (a tile
+ * owns the records that END in it), then each thread parses whole records out
+ * of shared memory.  Group keys are counted in a per-CTA shared-memory hash
+ * table (exact: key bytes are compared, hashes only pick the slot) that is
+ * flushed once per launch into the global table with 64-bit atomics.
+ * Input is read from HBM exactly once (+PRELAP/TILE overlap); no intermediate
+ * columns are written.
+ */
+#ifndef DNG_SCAN_KERNEL_CUH
+#define DNG_SCAN_KERNEL_CUH
+
+#include <cuda_runtime.h>
+#include "record.cuh"
+
+namespace dng {
+
+#ifndef DNG_NT
+#define DNG_NT 256			/* threads per CTA */
+#endif
+#ifndef DNG_TILE
+#define DNG_TILE 49152			/* bytes of input a tile owns */
+#endif
+#ifndef DNG_PRELAP
+#define DNG_PRELAP 4096			/* bytes staged before the tile */
+#endif
+#define DNG_CTAS_PER_SM 2
+#define DNG_NLCAP 2048			/* newline positions per pass */
+#define DNG_SSLOTS 256			/* shared hash table slots */
+#define DNG_SKEY 40			/* inline key bytes per shared slot */
+#define DNG_MAXREC (1u << 24)		/* longest line handled */
+
+enum { NCTR = 24 };
+enum {
+	CTR_LINES = 0, CTR_INVALID_JSON, CTR_INVALID_POINT,
+	CTR_DS_FILTERED, CTR_DS_FAILED, CTR_USER_FILTERED, CTR_USER_FAILED,
+	CTR_SYNTH_UNDEF, CTR_SYNTH_BADDATE, CTR_TIME_FILTERED, CTR_TIME_FAILED,
+	CTR_AGGR, CTR_SLOW, CTR_UNSUPPORTED, CTR_LONG
+};
+
+enum { ST_TABLE_FULL = 1, ST_ARENA_FULL = 2 };
+
+struct GEntry {
+	unsigned long long tag;		/* 0 empty, else hash | 1 */
+	unsigned long long count;
+	u32 koff;			/* key offset in arena + 1; 0 = unpublished */
+	u32 klen;
+};
+
+struct GTable {
+	GEntry *entries;
+	u8 *arena;
+	u32 *misc;			/* [0] arena cursor [1] nentries [2] status */
+	u32 mask;			/* capacity - 1 */
+	u32 arena_cap;
+};
+
+struct SSlot {
+	unsigned long long tag;
+	unsigned long long count;
+	u32 klen;
+	u32 pad;
+	u8 key[DNG_SKEY];
+};
+
+struct ScanArgs {
+	const u8 *data;			/* 16-byte aligned */
+	unsigned long long start;	/* first valid byte */
+	unsigned long long nbytes;	/* end of valid bytes */
+	const DevPlan *plan;
+	unsigned long long *counters;
+	GTable tab;
+	u32 ntiles;
+	u32 final;			/* treat an unterminated tail as a line */
+};
+
+#define DNG_READY 0x8000000000000000ull
+
+static constexpr size_t SMEM_PLAN = (sizeof (DevPlan) + 127) & ~(size_t)127;
+static constexpr size_t SMEM_TAB = sizeof (SSlot) * DNG_SSLOTS;
+static constexpr size_t SMEM_NL = sizeof (u32) * DNG_NLCAP;
+static constexpr size_t SMEM_DATA = DNG_PRELAP + DNG_TILE + 128;
+static constexpr size_t SMEM_TOTAL = SMEM_PLAN + SMEM_TAB + SMEM_NL + SMEM_DATA;
+
+/* ---- global table ------------------------------------------------------- */
+
+__device__ __forceinline__ void global_add(const GTable &t, u64 h,
+    const u8 *key, u32 klen, unsigned long long w)
+{
+	unsigned long long claim = h | 1ull;
+	u32 idx = (u32)(h >> 17) & t.mask;
+	for (u32 probe = 0; probe <= t.mask; probe++) {
+		GEntry *e = &t.entries[idx];
+		unsigned long long tag =
+		    *(volatile unsigned long long *)&e->tag;
+		if (tag == 0) {
+			unsigned long long old = atomicCAS(&e->tag, 0ull, claim);
+			if (old == 0) {
+				u32 need = (klen + 7) & ~7u;
+				u32 off = atomicAdd(&t.misc[0], need);
+				if (off + need > t.arena_cap) {
+					atomicOr(&t.misc[2], ST_ARENA_FULL);
+					off = 0;
+					klen = 0;
+				} else {
+					for (u32 k = 0; k < klen; k++)
+						t.arena[off + k] = key[k];
+				}
+				e->klen = klen;
+				__threadfence();
+				atomicExch(&e->koff, off + 1);
+				atomicAdd(&t.misc[1], 1u);
+				atomicAdd(&e->count, w);
+				return;
+			}
+			tag = old;
+		}
+		if (tag == claim) {
+			u32 koff;
+			while ((koff = *(volatile u32 *)&e->koff) == 0)
+				;
+			__threadfence();
+			if (*(volatile u32 *)&e->klen == klen) {
+				const u8 *s = t.arena + (koff - 1);
+				u32 k = 0;
+				while (k < klen && s[k] == key[k])
+					k++;
+				if (k == klen) {
+					atomicAdd(&e->count, w);
+					return;
+				}
+			}
+		}
+		idx = (idx + 1) & t.mask;
+	}
+	atomicOr(&t.misc[2], ST_TABLE_FULL);
+}
+
+/* ---- shared table --------------------------------------------------------- */
+
+__device__ __forceinline__ void shared_add(SSlot *tab, const GTable &gt, u64 h,
+    const u8 *key, u32 klen, unsigned long long w)
+{
+	if (klen <= DNG_SKEY) {
+		unsigned long long claim = (h | 1ull) & ~DNG_READY;
+		u32 idx = (u32)(h >> 40) & (DNG_SSLOTS - 1);
+		for (u32 probe = 0; probe < 16; probe++) {
+			SSlot *s = &tab[idx];
+			unsigned long long tag =
+			    *(volatile unsigned long long *)&s->tag;
+			if (tag == 0) {
+				unsigned long long old =
+				    atomicCAS(&s->tag, 0ull, claim);
+				if (old == 0) {
+					s->klen = klen;
+					for (u32 k = 0; k < klen; k++)
+						s->key[k] = key[k];
+					atomicAdd(&s->count, w);
+					__threadfence_block();
+					*(volatile unsigned long long *)&s->tag =
+					    claim | DNG_READY;
+					return;
+				}
+				tag = old;
+			}
+			if ((tag & ~DNG_READY) == claim) {
+				while (!(tag & DNG_READY))
+					tag = *(volatile unsigned long long *)
+					    &s->tag;
+				__threadfence_block();
+				if (*(volatile u32 *)&s->klen == klen) {
+					const volatile u8 *sk = s->key;
+					u32 k = 0;
+					while (k < klen && sk[k] == key[k])
+						k++;
+					if (k == klen) {
+						atomicAdd(&s->count, w);
+						return;
+					}
+				}
+			}
+			idx = (idx + 1) & (DNG_SSLOTS - 1);
+		}
+	}
+	global_add(gt, h, key, klen, w);
+}
+
+/* ---- TMA / mbarrier helpers ----------------------------------------------- */
+
+__device__ __forceinline__ u32 smem_u32(const void *p)
+{
+	return (u32)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
+	    :: "r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+	    :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src,
+    u32 bytes, u64 *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::"
+	    "complete_tx::bytes [%0], [%1], %2, [%3];"
+	    :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	    : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}\n"
+	    :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+/* exact per-byte equality mask: 0x80 in every byte of w equal to 0x0a */
+__device__ __forceinline__ u32 nl_mask(u32 w)
+{
+	u32 x = w ^ 0x0a0a0a0au;
+	u32 t = ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x;
+	return ~(t | 0x7f7f7f7fu);
+}
+
+/* ---- one record ----------------------------------------------------------- */
+
+__device__ __forceinline__ void scan_one(const u8 *rec, u32 len,
+    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C)
+{
+	RecState R;
+	u8 kbuf[KEY_MAX + 16];
+	C.lines++;
+	if (len >= DNG_MAXREC) {
+		C.unsupported++;
+		return;
+	}
+	parse_record(rec, len, P, R);
+	if (R.flags & RF_UNSUPPORTED)
+		C.unsupported++;
+	if (R.flags & RF_INVALID) {
+		C.invalid_json++;
+		return;
+	}
+	u32 klen;
+	u64 w;
+	if (process_record(rec, len, P, R, C, kbuf, klen, w)) {
+		u64 h = key_hash(kbuf, klen);
+		shared_add(stab, gt, h, kbuf, klen, w);
+	}
+}
+
+/* out-of-line copy for lines that begin before the staged window (rare):
+ * keeps the hot shared-memory instantiation of the parser small */
+__device__ __noinline__ void scan_one_global(const u8 *rec, u32 len,
+    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C)
+{
+	scan_one(rec, len, P, stab, gt, C);
+}
+
+/* ---- the kernel ------------------------------------------------------------ */
+
+__global__ void __launch_bounds__(DNG_NT, DNG_CTAS_PER_SM)
+scan_kernel(const ScanArgs a)
+{
+	extern __shared__ __align__(128) u8 smem[];
+	DevPlan *sp = (DevPlan *)smem;
+	SSlot *stab = (SSlot *)(smem + SMEM_PLAN);
+	u32 *nlpos = (u32 *)(smem + SMEM_PLAN + SMEM_TAB);
+	u8 *sdata = smem + SMEM_PLAN + SMEM_TAB + SMEM_NL;
+	__shared__ __align__(8) u64 mbar;
+	__shared__ u32 wsum[DNG_NT / 32];
+	__shared__ u32 s_total;
+	__shared__ u32 s_prev;		/* newline before the current pass */
+
+	const u32 tid = threadIdx.x;
+	const u32 lane = tid & 31, wid = tid >> 5;
+
+	{	/* plan -> shared, clear the table */
+		const uint4 *src = (const uint4 *)a.plan;
+		uint4 *dst = (uint4 *)sp;
+		for (u32 i = tid; i < sizeof (DevPlan) / 16; i += DNG_NT)
+			dst[i] = src[i];
+		uint4 z = make_uint4(0, 0, 0, 0);
+		uint4 *tz = (uint4 *)stab;
+		for (u32 i = tid; i < SMEM_TAB / 16; i += DNG_NT)
+			tz[i] = z;
+		if (tid == 0)
+			mbar_init(&mbar, 1);
+	}
+	__syncthreads();
+	const DevPlan &P = *sp;
+
+	LocalCounters C;
+	C.lines = C.invalid_json = C.invalid_point = 0;
+	C.ds_filtered = C.ds_failedeval = C.user_filtered = 0;
+	C.user_failedeval = C.synth_undef = C.synth_baddate = 0;
+	C.time_filtered = C.time_failedeval = C.aggr = C.slow = 0;
+	C.unsupported = 0;
+	u32 nlong = 0;
+	u32 parity = 0;
+
+	for (u32 tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+		const unsigned long long g0 = (unsigned long long)tile * DNG_TILE;
+		const unsigned long long ws = g0 >= DNG_PRELAP ?
+		    g0 - DNG_PRELAP : 0;
+		unsigned long long we = g0 + DNG_TILE;
+		if (we > a.nbytes)
+			we = a.nbytes;
+		const u32 wlen = (u32)(we - ws);
+		const u32 bulk = wlen & ~15u;
+		const u32 off0 = (u32)(g0 - ws);	/* tile start in window */
+
+		if (tid == 0 && bulk) {
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			mbar_expect_tx(&mbar, bulk);
+			tma_load_1d(sdata, a.data + ws, bulk, &mbar);
+		}
+		for (u32 i = bulk + tid; i < wlen; i += DNG_NT)
+			sdata[i] = a.data[ws + i];
+		if (bulk) {
+			mbar_wait(&mbar, parity);
+			parity ^= 1;
+		}
+		__syncthreads();
+
+		/* lowest window offset that holds valid input */
+		const u32 lower = a.start > ws ? (u32)(a.start - ws) : 0;
+		/* this thread's slice of the tile, 16-byte words */
+		const u32 CH = DNG_TILE / DNG_NT;
+		u32 c0 = off0 + tid * CH, c1 = c0 + CH;
+		if (c1 > wlen)
+			c1 = wlen;
+		u32 cnt = 0;
+		for (u32 p = c0; p < c1; p += 16) {
+			uint4 v = *(const uint4 *)(sdata + p);
+			u32 m0 = nl_mask(v.x), m1 = nl_mask(v.y);
+			u32 m2 = nl_mask(v.z), m3 = nl_mask(v.w);
+			if (p + 16 > c1 || p < lower) {
+				/* partial word: count byte by byte */
+				u32 e = c1 - p < 16 ? c1 - p : 16;
+				for (u32 k = 0; k < e; k++)
+					if (p + k >= lower &&
+					    sdata[p + k] == '\n')
+						cnt++;
+			} else {
+				cnt += __popc(m0) + __popc(m1) + __popc(m2) +
+				    __popc(m3);
+			}
+		}
+		/* an unterminated final line ends at a virtual newline */
+		const bool vnl = a.final && we == a.nbytes && tid == DNG_NT - 1 &&
+		    a.nbytes > a.start && wlen > 0 && wlen > lower &&
+		    sdata[wlen - 1] != '\n';
+		if (vnl)
+			cnt++;
+
+		/* block exclusive scan of cnt */
+		u32 incl = cnt;
+		for (int d = 1; d < 32; d <<= 1) {
+			u32 y = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= (u32)d)
+				incl += y;
+		}
+		if (lane == 31)
+			wsum[wid] = incl;
+		__syncthreads();
+		if (wid == 0) {
+			u32 s = lane < DNG_NT / 32 ? wsum[lane] : 0;
+			u32 si = s;
+			for (int d = 1; d < 32; d <<= 1) {
+				u32 y = __shfl_up_sync(0xffffffffu, si, d);
+				if (lane >= (u32)d)
+					si += y;
+			}
+			if (lane < DNG_NT / 32)
+				wsum[lane] = si - s;
+			if (lane == DNG_NT / 32 - 1)
+				s_total = si;
+		}
+		__syncthreads();
+		const u32 mybase = wsum[wid] + incl - cnt;
+		const u32 total = s_total;
+
+		for (u32 pass = 0; pass < total; pass += DNG_NLCAP) {
+			/* write this pass's newline positions, in order */
+			u32 idx = mybase;
+			if (idx < pass + DNG_NLCAP && idx + cnt > pass) {
+				for (u32 p = c0; p < c1; p++) {
+					if (p >= lower && sdata[p] == '\n') {
+						if (idx >= pass &&
+						    idx < pass + DNG_NLCAP)
+							nlpos[idx - pass] = p;
+						idx++;
+					}
+				}
+				if (vnl && idx >= pass && idx < pass + DNG_NLCAP)
+					nlpos[idx - pass] = wlen;
+			}
+			__syncthreads();
+			u32 n = total - pass;
+			if (n > DNG_NLCAP)
+				n = DNG_NLCAP;
+			for (u32 r = tid; r < n; r += DNG_NT) {
+				u32 end = nlpos[r];
+				u32 beg;
+				bool islong = false;
+				if (r > 0) {
+					beg = nlpos[r - 1] + 1;
+				} else if (pass > 0) {
+					beg = s_prev + 1;
+				} else {
+					u32 p = off0 < lower ? lower : off0;
+					if (p > end)
+						p = end;
+					while (p > lower && sdata[p - 1] != '\n')
+						p--;
+					beg = p;
+					if (p == lower && ws + lower > a.start &&
+					    (p == 0 || sdata[p - 1] != '\n'))
+						islong = true;
+				}
+				if (!islong) {
+					scan_one(sdata + beg, end - beg, P, stab,
+					    a.tab, C);
+				} else {
+					/* the line began before the staged
+					 * window: find its start in HBM and
+					 * parse it from there */
+					unsigned long long q = ws + lower;
+					while (q > a.start &&
+					    a.data[q - 1] != '\n')
+						q--;
+					nlong++;
+					scan_one_global(a.data + q,
+					    (u32)min((unsigned long long)
+					    DNG_MAXREC, ws + end - q), P, stab,
+					    a.tab, C);
+				}
+			}
+			__syncthreads();
+			if (tid == 0)
+				s_prev = nlpos[n - 1];
+			__syncthreads();
+		}
+		__syncthreads();
+	}
+
+	/* flush the shared table into the global one */
+	__syncthreads();
+	for (u32 i = tid; i < DNG_SSLOTS; i += DNG_NT) {
+		SSlot *s = &stab[i];
+		if (s->tag != 0) {
+			/* slots are zero-initialised and written once, so
+			 * s->key is already zero padded for key_hash() */
+			global_add(a.tab, key_hash(s->key, s->klen), s->key,
+			    s->klen, s->count);
+		}
+	}
+
+	/* counters: warp reduce, one atomic per warp per counter */
+	u32 vals[NCTR];
+	for (int k = 0; k < NCTR; k++)
+		vals[k] = 0;
+	vals[CTR_LINES] = C.lines;
+	vals[CTR_INVALID_JSON] = C.invalid_json;
+	vals[CTR_INVALID_POINT] = C.invalid_point;
+	vals[CTR_DS_FILTERED] = C.ds_filtered;
+	vals[CTR_DS_FAILED] = C.ds_failedeval;
+	vals[CTR_USER_FILTERED] = C.user_filtered;
+	vals[CTR_USER_FAILED] = C.user_failedeval;
+	vals[CTR_SYNTH_UNDEF] = C.synth_undef;
+	vals[CTR_SYNTH_BADDATE] = C.synth_baddate;
+	vals[CTR_TIME_FILTERED] = C.time_filtered;
+	vals[CTR_TIME_FAILED] = C.time_failedeval;
+	vals[CTR_AGGR] = C.aggr;
+	vals[CTR_SLOW] = C.slow;
+	vals[CTR_UNSUPPORTED] = C.unsupported;
+	vals[CTR_LONG] = nlong;
+#pragma unroll
+	for (int k = 0; k <= CTR_LONG; k++) {
+		u32 v = vals[k];
+		for (int d = 16; d > 0; d >>= 1)
+			v += __shfl_xor_sync(0xffffffffu, v, d);
+		if (lane == 0 && v)
+			atomicAdd(&a.counters[k], (unsigned long long)v);
+	}
+}
+
+/* gather occupied entries: out[i] = {koff-1, klen, count} */
+struct OutEntry {
+	unsigned long long count;
+	u32 koff, klen;
+};
+
+__global__ void compact_kernel(const GEntry *entries, u32 cap, OutEntry *out,
+    u32 *nout)
+{
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap;
+	    i += gridDim.x * blockDim.x) {
+		if (entries[i].tag != 0) {
+			u32 p = atomicAdd(nout, 1u);
+			out[p].count = entries[i].count;
+			out[p].koff = entries[i].koff - 1;
+			out[p].klen = entries[i].klen;
+		}
+	}
+}
+
+/* first and last '\n' in data[lo, hi): *first = min pos, *last = max pos + 1 */
+__global__ void find_nl_kernel(const u8 *data, unsigned long long lo,
+    unsigned long long hi, unsigned long long *first, unsigned long long *last)
+{
+	for (unsigned long long i = lo + blockIdx.x * (unsigned long long)
+	    blockDim.x + threadIdx.x; i < hi;
+	    i += (unsigned long long)gridDim.x * blockDim.x) {
+		if (data[i] == '\n') {
+			atomicMin(first, i);
+			atomicMax(last, i + 1);
+		}
+	}
+}
+
+} /* namespace dng */
+#endif

@@ -447,6 +447,8 @@ def iter_lines(chunks):
 
 
 def _bump(counters, stage, name, n=1):
+    if not n:
+        return
     counters.setdefault(stage, {})
     counters[stage][name] = counters[stage].get(name, 0) + n
 
@@ -490,7 +492,8 @@ def scan(plan, chunks):
             f = obj.get(b'fields') if isinstance(obj, dict) else None
             w = obj.get(b'value') if isinstance(obj, dict) else None
             if not isinstance(f, dict) or not isinstance(w, float) or \
-                    isinstance(w, bool) or w != int(w) or w < 0:
+                    isinstance(w, bool) or math.isinf(w) or w != int(w) or \
+                    w < 0 or w > 2.0 ** 53:
                 # the reference asserts here; we count and drop (unpinned)
                 _bump(counters, 'json parser', 'invalid point')
                 continue
