@@ -1,0 +1,159 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  These run on
+the B200 box only (`-m gpu`); nothing here reads /root/reference."""
+
+import ctypes
+import hashlib
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import corpus  # noqa: E402
+from engines import canon_points, py_engine  # noqa: E402
+from golden_harness import check_section  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_engine(plan, files):
+    from dragnet_b200 import datasource_gpu
+    r = datasource_gpu.run_plan(plan, files=files)
+    return r.points, r.counters
+
+
+def gpu_engine_chunks(plan, data, chunk):
+    from dragnet_b200 import datasource_gpu
+    chunks = [data[i:i + chunk] for i in range(0, len(data), chunk)]
+    r = datasource_gpu.run_plan(plan, chunks=chunks)
+    return r.points, r.counters
+
+
+@pytest.mark.parametrize('suite', ['scan_file', 'scan_fileset', 'empty',
+                                   'scan_manta'])
+def test_reference_goldens_through_c_abi(suite, goldens, datadir):
+    n = 0
+    for i, sec in enumerate(goldens['suites'][suite]):
+        if sec['cmd'] != 'scan':
+            continue
+        if suite == 'scan_manta' and ('--counters' in sec['argv'] or
+                                      '--dry-run' in sec['argv'] or
+                                      '-n' in sec['argv']):
+            continue
+        check_section(gpu_engine, suite, i, sec, datadir)
+        n += 1
+    assert n >= 8
+
+
+def _write(tmp_path, name, lines, final_newline=True):
+    p = tmp_path / name
+    p.write_bytes(b'\n'.join(lines) + (b'\n' if final_newline else b''))
+    return str(p)
+
+
+@pytest.mark.parametrize('qi', range(len(corpus.EDGE_QUERIES)))
+def test_edge_lines(qi, tmp_path):
+    argv, ds = corpus.EDGE_QUERIES[qi]
+    plan = corpus.make_plan(argv, ds)
+    path = _write(tmp_path, 'edge.log', corpus.EDGE_LINES)
+    exp_p, exp_c = py_engine(plan, [path])
+    act_p, act_c = gpu_engine(plan, [path])
+    assert canon_points(act_p) == canon_points(exp_p)
+    assert act_c == exp_c
+
+
+@pytest.mark.parametrize('qi', range(len(corpus.SKINNER_QUERIES)))
+def test_skinner_lines(qi, tmp_path):
+    argv, ds = corpus.SKINNER_QUERIES[qi]
+    plan = corpus.make_plan(argv, ds)
+    path = _write(tmp_path, 'sk.log', corpus.SKINNER_LINES)
+    exp_p, exp_c = py_engine(plan, [path])
+    act_p, act_c = gpu_engine(plan, [path])
+    assert canon_points(act_p) == canon_points(exp_p)
+    assert act_c == exp_c
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_random_lines(seed, tmp_path):
+    path = _write(tmp_path, 'rand.log', corpus.random_lines(seed, 3000),
+                  final_newline=(seed % 2 == 0))
+    for argv, ds in corpus.EDGE_QUERIES[::4]:
+        plan = corpus.make_plan(argv, ds)
+        exp_p, exp_c = py_engine(plan, [path])
+        act_p, act_c = gpu_engine(plan, [path])
+        assert canon_points(act_p) == canon_points(exp_p), argv
+        assert act_c == exp_c, argv
+
+
+def test_chunk_boundaries_do_not_matter(tmp_path):
+    """lstream carries partial lines across arbitrary chunk boundaries."""
+    from dragnet_b200 import native
+    data = native.gen_host(native.gen_params(total_records=3000), 0, 3000)
+    data += b'{"req":{"method":"TAIL"}}'          # unterminated last line
+    plan = corpus.make_plan(['-b', 'req.method,res.statusCode'])
+    ref = None
+    for chunk in (len(data), 1 << 16, 4099, 257, 31):
+        pts, ctr = gpu_engine_chunks(plan, data, chunk)
+        if ref is None:
+            ref = (canon_points(pts), ctr)
+            assert ctr['json parser']['ninputs'] == 3001
+        assert (canon_points(pts), ctr) == ref, chunk
+
+
+@pytest.mark.parametrize('name', sorted(corpus.BASELINE_QUERIES))
+def test_synthetic_matches_oracle(name, tmp_path):
+    """BASELINE.json query shapes on mktestdata-shaped input, vs the oracle."""
+    from dragnet_b200 import native
+    n = 20000
+    data = native.gen_host(native.gen_params(total_records=n), 0, n)
+    p = tmp_path / 'syn.log'
+    p.write_bytes(data)
+    argv, ds = corpus.BASELINE_QUERIES[name]
+    plan = corpus.make_plan(argv, ds)
+    exp_p, exp_c = py_engine(plan, [str(p)])
+    act_p, act_c = gpu_engine(plan, [str(p)])
+    assert canon_points(act_p) == canon_points(exp_p)
+    assert act_c == exp_c
+
+
+def test_device_generator_is_byte_identical_and_feed_device_matches():
+    import torch
+    from dragnet_b200 import datasource_gpu, native
+    n = 200000
+    params = native.gen_params(total_records=n)
+    host = native.gen_host(params, 0, n)
+    cap = n * 320
+    buf = torch.empty(cap, dtype=torch.uint8, device='cuda:0')
+    ln = ctypes.c_size_t()
+    rc = native.lib().dng_gen_device(ctypes.byref(params), 0, 0, n,
+                                     buf.data_ptr(), cap, ctypes.byref(ln))
+    assert rc == 0
+    assert ln.value == len(host)
+    dev = bytes(buf[:ln.value].cpu().numpy().tobytes())
+    assert hashlib.sha256(dev).digest() == hashlib.sha256(host).digest()
+    plan = corpus.make_plan(['-b', 'operation,req.method,host'])
+    a = datasource_gpu.run_plan(plan, device_buffers=[(buf.data_ptr(),
+                                                       ln.value)])
+    b = datasource_gpu.run_plan(plan, chunks=[host])
+    assert canon_points(a.points) == canon_points(b.points)
+    assert a.flat_counters['lines'] == n
+    # split device feed at an arbitrary (unaligned-to-line) 16-byte boundary
+    cut = (ln.value // 3) & ~15
+    c = datasource_gpu.run_plan(plan, device_buffers=[
+        (buf.data_ptr(), cut), (buf.data_ptr() + cut, ln.value - cut)])
+    assert canon_points(c.points) == canon_points(b.points)
+    assert c.flat_counters['lines'] == n
+
+
+def test_long_lines_and_large_counts(tmp_path):
+    """Lines longer than the staged window take the HBM path; many small
+    lines exercise the multi-pass newline index."""
+    lines = [b'{"a":"s","pad":"' + b'p' * 70000 + b'"}',
+             b'{"pad":"' + b'q' * 200000 + b'","a":"t"}'] + [b'{"a":1}'] * 50000
+    lines += [b''] * 30000 + [b'{"a":"s"}']
+    path = _write(tmp_path, 'long.log', lines)
+    plan = corpus.make_plan(['-b', 'a'])
+    exp_p, exp_c = py_engine(plan, [path])
+    act_p, act_c = gpu_engine(plan, [path])
+    assert canon_points(act_p) == canon_points(exp_p)
+    assert act_c == exp_c
