@@ -971,10 +971,8 @@ DNG_HD int process_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R,
 				nerr++;
 				continue;
 			}
-			/* Math.floor(parsed / 1000) */
-			int64_t sec = ms >= 0 ? ms / 1000 :
-			    -((-ms + 999) / 1000);
-			R.syn[j] = (double)sec;
+			/* Math.floor(parsed / 1000), in binary64 like JS */
+			R.syn[j] = floor((double)ms / 1000.0);
 		}
 		if (nerr)
 			goto dropped;

@@ -526,7 +526,7 @@ def scan(plan, chunks):
                             _bump(counters, 'Datetime parser', 'baddate')
                         nerrors += 1
                         continue
-                    parsed = float(ms // 1000)
+                    parsed = float(math.floor(ms / 1000.0))
                 if isinstance(point['fields'], (dict, list)):
                     point['synth'][sc['name'].encode('utf-8')] = parsed
             if nerrors:

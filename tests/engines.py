@@ -137,6 +137,41 @@ def hostcheck_engine(plan, files):
     return points, staged_counters(plan, doc['counters'], len(points))
 
 
+def build_cpp_oracle():
+    subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle')])
+    return os.path.join(ROOT, 'oracle', 'dn_oracle_cpp')
+
+
+def _decode_doc(plan, doc):
+    points = []
+    for p in doc['points']:
+        fields = []
+        for b, col in zip(plan['breakdowns'], p['cols']):
+            if 's' in col:
+                fields.append((b['name'], bytes.fromhex(col['s'])))
+            else:
+                fields.append((b['name'], struct.unpack(
+                    '<d', struct.pack('<Q', int(col['n'], 16)))[0]))
+        points.append((fields, p['value']))
+    return points, staged_counters(plan, doc['counters'], len(points))
+
+
+def cpp_engine(plan, files, threads=1):
+    """oracle/dn_oracle.cpp (DOM-based C++ restatement; also the CPU
+    baseline bench.py times)."""
+    exe = build_cpp_oracle()
+    with tempfile.NamedTemporaryFile('w', suffix='.json', delete=False) as f:
+        json.dump(plan, f)
+        pf = f.name
+    try:
+        out = subprocess.run([exe, pf, '--threads', str(threads)] +
+                             list(files), capture_output=True,
+                             check=True).stdout
+    finally:
+        os.unlink(pf)
+    return _decode_doc(plan, json.loads(out))
+
+
 def canon_points(points):
     """Order-independent, NaN-safe form for comparing two engines."""
     out = []
