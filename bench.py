@@ -1,0 +1,501 @@
+#!/usr/bin/env python
+"""bench.py: the headline benchmark -- JSON records/s scanned+aggregated.
+
+  python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
+
+Workload (BASELINE.json configs[1]): 100 M rows of mktestdata-shaped NDJSON per
+GPU (~22.4 GB, generated on the device, deterministic), `dn scan -b req.method`.
+A step is one full scan of the shard (+ the NCCL merge of the tallies when
+N > 1).  `value` = records of all ranks / device time with the input resident in
+HBM; `e2e` = the same scan fed from pinned HOST buffers through the public C
+ABI (dng_scan_feed_pinned: H2D inside the timed region); `roofline` = algorithmic
+input bytes / scan-kernel time (CUDA events on the launch stream) against the
+measured HBM copy peak; `cpu_baseline` = oracle/dn_oracle.cpp (restated CPU
+reference: node + the reference's npm dependencies do not exist in this image)
+on a bounded sample, all host threads.  Inputs (22 GB) are far larger than L2
+(126 MB), so no explicit L2 flush is needed between iterations.
+"""
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+QUERIES = {
+    'C2': (['-b', 'req.method'], None,
+           'configs[1]: 100M-row synthetic NDJSON, -b req.method'),
+    'C3': (['-b', 'req.method,res.statusCode', '-f',
+            '{"eq":["req.method","GET"]}'], None,
+           'configs[2]: 100M rows, -b req.method,res.statusCode + krill eq'),
+    'C4': (['-b', 'latency[aggr=quantize]'], None,
+           'configs[3]: -b latency[aggr=quantize]'),
+    'C5': (['-b', 'operation,req.method,host'], None,
+           'configs[4]: 3-key breakdown, NCCL final reduce'),
+}
+
+
+def make_plan(argv, ds=None):
+    from dragnet_b200 import dn as mod_dn
+    from dragnet_b200 import query as mod_query
+    ds = ds or {}
+    options = mod_dn.dnParseArgs(list(argv))
+    q = mod_dn.dnQueryConfig(options)['query']
+    return mod_query.scan_plan(q, ds_filter=ds.get('filter'),
+                               time_field=ds.get('timeField'))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured'
+        except Exception:
+            pass
+    return 6650.0, 'fallback'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,'
+         'clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [],
+                    'samples': 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for l in self.lines:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None,
+                'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def canon(points):
+    return sorted((tuple(repr(c) for c in cols), v) for cols, v in points)
+
+
+# ---------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline
+# ---------------------------------------------------------------------------
+
+def oracle_exe():
+    exe = os.path.join(ROOT, 'oracle', 'dn_oracle_cpp')
+    if not os.path.exists(exe):
+        subprocess.check_call(['make', '-s', '-C',
+                               os.path.join(ROOT, 'oracle')])
+    return exe
+
+
+def run_oracle(plan, path, threads, repeat=1):
+    with tempfile.NamedTemporaryFile('w', suffix='.json', delete=False) as f:
+        json.dump(plan, f)
+        pf = f.name
+    try:
+        out = subprocess.run([oracle_exe(), pf, '--threads', str(threads),
+                              '--repeat', str(repeat), path],
+                             capture_output=True, check=True).stdout
+    finally:
+        os.unlink(pf)
+    return json.loads(out)
+
+
+def sample_file(rows, seed):
+    """A bounded sample of the workload written to tmpfs (host generator:
+    byte-identical to the device generator)."""
+    from dragnet_b200 import native
+    d = '/dev/shm' if os.path.isdir('/dev/shm') else tempfile.gettempdir()
+    path = os.path.join(d, 'dnbench_sample_%d_%d.ndjson' % (seed, rows))
+    if not os.path.exists(path):
+        params = native.gen_params(seed=seed, total_records=rows)
+        with open(path + '.tmp', 'wb') as f:
+            step = 250000
+            for first in range(0, rows, step):
+                f.write(native.gen_host(params, first,
+                                        min(step, rows - first)))
+        os.rename(path + '.tmp', path)
+    return path
+
+
+def oracle_points(doc):
+    import struct
+    pts = []
+    for p in doc['points']:
+        cols = []
+        for c in p['cols']:
+            if 's' in c:
+                cols.append(bytes.fromhex(c['s']))
+            else:
+                cols.append(struct.unpack('<d', struct.pack(
+                    '<Q', int(c['n'], 16)))[0])
+        pts.append((cols, p['value']))
+    return pts
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the restated CPU reference (oracle/dn_oracle.cpp) on
+    all host threads; a step = one scan of a bounded sample of the workload."""
+    if rank != 0:
+        return
+    argv, ds, desc = QUERIES[args.query]
+    plan = make_plan(argv, ds)
+    threads = os.cpu_count() or 1
+    rows = args.cpu_rows
+    path = sample_file(rows, 0xD5A60000)
+    for _ in range(max(args.warmup, 1)):
+        run_oracle(plan, path, threads)
+    secs = []
+    for _ in range(args.steps):
+        secs.append(run_oracle(plan, path, threads)['seconds'])
+    per = sum(secs) / len(secs)
+    value = rows / per
+    line = {
+        'impl': 'reference', 'metric': 'json_records_per_sec',
+        'value': value, 'unit': 'records/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': per * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
+        'data': 'synthetic',
+        'config': {'workload': desc, 'rows_per_step': rows,
+                   'query': ' '.join(argv),
+                   'note': 'CPU reference arm: C++ restatement of the '
+                           'reference Node.js scan path (node and the '
+                           "reference's npm dependencies are not in this "
+                           'image); bounded sample of the 100M-row workload'},
+        'cpu_baseline': {'value': value, 'unit': 'records/s',
+                         'cores': threads, 'kind': 'port',
+                         'sample': '%d rows (%.2f GB) of the workload, %d '
+                                   'threads, file-range sharded' %
+                                   (rows, os.path.getsize(path) / 1e9,
+                                    threads)},
+        'e2e': {'value': value, 'unit': 'records/s',
+                'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+
+def gpu_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from dragnet_b200 import native
+
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', dev))
+    L = native.lib()
+    argv, ds, desc = QUERIES[args.query]
+    plan = make_plan(argv, ds)
+    plan_json = json.dumps(plan, separators=(',', ':'))
+    rows = args.rows
+    seed = 0xD5A60000 + rank
+
+    # ---- the shard, generated in HBM --------------------------------------
+    params = native.gen_params(seed=seed, total_records=rows)
+    cap = rows * 226 + (64 << 20)
+    buf = torch.empty(cap, dtype=torch.uint8, device='cuda:%d' % dev)
+    nbytes = 0
+    chunk = 4000000
+    ln = ctypes.c_size_t()
+    pool_rows = min(args.pool_rows, rows)
+    for first in range(0, rows, chunk):
+        cnt = min(chunk, rows - first)
+        rc = L.dng_gen_device(ctypes.byref(params), dev, first, cnt,
+                              buf.data_ptr() + nbytes, cap - nbytes,
+                              ctypes.byref(ln))
+        if rc != 0:
+            raise RuntimeError('dng_gen_device failed: %d' % rc)
+        nbytes += ln.value
+    torch.cuda.synchronize()
+
+    # ---- NCCL communicator of the library (id exchanged with torch) --------
+    comm = None
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = ctypes.create_string_buffer(128)
+            if L.dng_comm_unique_id(raw) != 0:
+                raise RuntimeError('dng_comm_unique_id failed')
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8)
+        idg = idbuf.cuda(dev)
+        dist.broadcast(idg, 0)
+        ident = bytes(idg.cpu().numpy().tobytes())
+        comm = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(256)
+        rc = L.dng_comm_init(ctypes.byref(comm), world, rank, ident, dev, err,
+                             256)
+        if rc != 0:
+            raise RuntimeError('dng_comm_init: %s' % err.value)
+
+    stream = torch.cuda.current_stream().cuda_stream
+    p_handle = native.Plan(plan_json)
+
+    def one_scan(feed, merge=True):
+        """-> (points or None, counters, kernel stats, device ms)"""
+        s = native.Scan(p_handle, dev)
+        s.set_stream(stream)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        feed(s)
+        if comm is not None and merge:
+            out = ctypes.c_void_p()
+            ctr = native.DngCounters()
+            rc = L.dng_merge_nccl(s.handle, comm, 0, ctypes.byref(out),
+                                  ctypes.byref(ctr))
+            if rc != 0:
+                raise RuntimeError('dng_merge_nccl: %d %s' %
+                                   (rc, L.dng_scan_error(s.handle)))
+            pts = native.Result(out).points() if out.value else None
+            counters = ctr.as_dict()
+        else:
+            res = s.finish()
+            pts = res.points()
+            counters = s.counters()
+        e1.record()
+        e1.synchronize()
+        st = s.kernel_stats()
+        ms = e0.elapsed_time(e1)
+        s.close()
+        return pts, counters, st, ms
+
+    def feed_resident(s):
+        s.feed_device(buf.data_ptr(), nbytes)
+
+    # ---- pinned host pool for the end-to-end leg ------------------------------
+    # the first pool_rows records of the shard, copied out of HBM once; their
+    # byte length is what the generator reports for that record range
+    tmp = torch.empty(pool_rows * 226 + (1 << 20), dtype=torch.uint8,
+                      device='cuda:%d' % dev)
+    rc = L.dng_gen_device(ctypes.byref(params), dev, 0, pool_rows,
+                          tmp.data_ptr(), tmp.numel(), ctypes.byref(ln))
+    assert rc == 0
+    pool_len = ln.value
+    del tmp
+    host_pool = torch.empty(pool_len, dtype=torch.uint8, pin_memory=True)
+    host_pool.copy_(buf[:pool_len])
+    torch.cuda.synchronize()
+    cycles = max(1, rows // pool_rows)
+    e2e_rows = cycles * pool_rows
+
+    def feed_host(s):
+        for _ in range(cycles):
+            s.feed_pinned(host_pool.data_ptr(), pool_len)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(feed, steps, warmup):
+        res = None
+        for _ in range(warmup):
+            res = one_scan(feed)
+        barrier()
+        sampler = ClockSampler(dev)
+        sampler.start()
+        t0 = time.perf_counter()
+        dev_ms, kern_ms, kern_bytes, launches = 0.0, 0.0, 0, 0
+        for _ in range(steps):
+            res = one_scan(feed)
+            dev_ms += res[3]
+            kern_ms += res[2]['kernel_ms']
+            kern_bytes += res[2]['kernel_bytes']
+            launches += res[2]['launches']
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64,
+                         device='cuda:%d' % dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {'dev_ms': float(t[0]), 'wall_ms': float(t[1]),
+                'kernel_ms': kern_ms, 'kernel_bytes': kern_bytes,
+                'launches': launches, 'clocks': clocks, 'last': res}
+
+    # ---- value: input resident in HBM -------------------------------------------
+    R = timed(feed_resident, args.steps, args.warmup)
+    ms_per_step = R['dev_ms'] / args.steps
+    total_rows = rows * world
+    value = total_rows / (ms_per_step / 1e3)
+
+    # ---- e2e: host buffers through the public C ABI ------------------------------
+    E = timed(feed_host, max(1, args.e2e_steps), 1)
+    e2e_ms = E['dev_ms'] / max(1, args.e2e_steps)
+    e2e_value = e2e_rows * world / (e2e_ms / 1e3)
+    result_bytes = 0
+    if E['last'][0] is not None:
+        result_bytes = sum(8 + sum(len(c) if isinstance(c, bytes) else 8
+                                   for c in cols)
+                           for cols, _ in E['last'][0])
+
+    if rank != 0:
+        if comm is not None:
+            L.dng_comm_destroy(comm)
+            dist.destroy_process_group()
+        return
+
+    # ---- parity + cpu_baseline on a bounded sample (rank 0, N=1 only) --------------
+    parity = None
+    cpu = None
+    if world == 1 and args.cpu_rows > 0:
+        srows = min(args.cpu_rows, rows)
+        path = sample_file(srows, seed)
+        threads = os.cpu_count() or 1
+        doc = run_oracle(plan, path, threads, repeat=2)
+        sample = open(path, 'rb').read()
+        # the same bytes through the GPU path
+        sbuf = torch.frombuffer(bytearray(sample), dtype=torch.uint8).cuda(dev)
+        g = one_scan(lambda s: s.feed_device(sbuf.data_ptr(), len(sample)),
+                     merge=False)
+        parity = 'exact' if canon(g[0]) == canon(oracle_points(doc)) and \
+            g[1]['lines'] == doc['counters']['lines'] else 'MISMATCH'
+        # the resident buffer starts with exactly these bytes
+        assert bytes(buf[:4096].cpu().numpy().tobytes()) == sample[:4096]
+        cpu = {'value': srows / doc['seconds'], 'unit': 'records/s',
+               'cores': threads, 'kind': 'port',
+               'sample': 'first %d rows (%.2f GB) of the workload, %d '
+                         'threads, best of 2; restated CPU oracle '
+                         '(oracle/dn_oracle.cpp): the reference Node path is '
+                         'not executable here (no node in the image)' %
+                         (srows, len(sample) / 1e9, threads)}
+
+    peak, how = measured_peaks()
+    n_launch = max(1, R['launches'])
+    achieved = (R['kernel_bytes'] / 1e9) / (R['kernel_ms'] / 1e3)
+    line = {
+        'metric': 'json_records_per_sec', 'value': value,
+        'unit': 'records/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_per_step,
+        'wall_ms_per_step': R['wall_ms'] / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'u8', 'data': 'synthetic',
+        'config': {
+            'workload': desc, 'rows_per_gpu': rows,
+            'bytes_per_gpu': nbytes, 'query': ' '.join(argv),
+            'parallelism': 'shard-per-gpu x%d, one NCCL reduce of the '
+                           'tallies' % world if world > 1 else 'single gpu',
+            'l2': 'inputs (%.1f GB) >> L2 (126 MB): no flush needed' %
+                  (nbytes / 1e9),
+            'points': len(R['last'][0]) if R['last'][0] is not None else None,
+        },
+        'roofline': {
+            'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+            'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+            'kernel': 'dng::scan_kernel',
+            'bytes_per_launch': R['kernel_bytes'] / n_launch,
+            'ms_per_launch': R['kernel_ms'] / n_launch,
+            'peak_source': '%s HBM copy bandwidth (MEASURED_PEAKS.json)' % how,
+        },
+        'e2e': {'value': e2e_value, 'unit': 'records/s',
+                'h2d_bytes_per_step': cycles * pool_len,
+                'd2h_bytes_per_step': result_bytes,
+                'ms_per_step': e2e_ms,
+                'h2d_gbs': cycles * pool_len / 1e9 / (e2e_ms / 1e3),
+                'note': 'pinned host pool of %d rows fed %dx per step via '
+                        'dng_scan_feed_pinned (H2D ring overlapped with the '
+                        'scan kernel)' % (pool_rows, cycles)},
+        'gpu_launches': R['launches'],
+        'clocks': R['clocks'],
+        'parity': parity,
+    }
+    if cpu:
+        line['cpu_baseline'] = cpu
+    print(json.dumps(line), flush=True)
+    if comm is not None:
+        L.dng_comm_destroy(comm)
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--query', default='C2', choices=sorted(QUERIES))
+    ap.add_argument('--rows', type=int,
+                    default=int(os.environ.get('DNG_BENCH_ROWS', 100000000)))
+    ap.add_argument('--pool-rows', type=int, default=10000000)
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--cpu-rows', type=int, default=4000000)
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    import __graft_entry__
+    from dragnet_b200 import native
+    oexe = os.path.join(ROOT, 'oracle', 'dn_oracle_cpp')
+    if rank == 0:
+        if not (os.path.exists(native.LIB_PATH) and os.path.exists(oexe)):
+            __graft_entry__.build()
+    else:
+        t0 = time.time()
+        while not os.path.exists(native.LIB_PATH) and time.time() - t0 < 600:
+            time.sleep(1)
+    if args.impl == 'reference':
+        reference_arm(args, rank, world)
+        return 0
+    gpu_arm(args, rank, local_rank, world)
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

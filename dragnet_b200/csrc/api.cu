@@ -56,6 +56,7 @@ struct dng_scan {
 	int device = 0;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	cudaStream_t own_stream = nullptr;
 	DevPlan *d_plan = nullptr;
 	GTable tab{};
 	unsigned long long *d_counters = nullptr;
@@ -290,6 +291,7 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		if ((rc = s->cuda(cudaStreamCreateWithFlags(&s->stream,
 		    cudaStreamNonBlocking), "cudaStreamCreate")))
 			break;
+		s->own_stream = s->stream;
 		if ((rc = s->cuda(cudaStreamCreateWithFlags(&s->copy_stream,
 		    cudaStreamNonBlocking), "cudaStreamCreate")))
 			break;
@@ -338,6 +340,16 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 	}
 	*out = s;
 	set_err(err, errlen, "");
+	return DNG_OK;
+}
+
+int dng_scan_set_stream(dng_scan *s, void *cuda_stream)
+{
+	if (!s)
+		return DNG_EINVAL;
+	if (s->launches || s->bytes_fed)
+		return s->fail(DNG_EINVAL, "dng_scan_set_stream after a feed");
+	s->stream = (cudaStream_t)cuda_stream;
 	return DNG_OK;
 }
 
@@ -703,8 +715,8 @@ void dng_scan_destroy(dng_scan *s)
 	cudaFree(s->d_nl);
 	cudaFree(s->d_carry);
 	cudaFree(s->d_side);
-	if (s->stream)
-		cudaStreamDestroy(s->stream);
+	if (s->own_stream)
+		cudaStreamDestroy(s->own_stream);
 	if (s->copy_stream)
 		cudaStreamDestroy(s->copy_stream);
 	delete s;

@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -27,6 +28,7 @@
 
 #include "../../include/dragnet_gpu.h"
 #include "result.h"
+#include "plan.h"
 
 namespace {
 
@@ -68,6 +70,69 @@ std::string dict_serialize(const std::vector<std::string> &keys)
 } /* namespace */
 
 extern "C" {
+
+int dng_result_from_points(const dng_plan *plan, size_t npoints,
+    const char *const *strs, const size_t *strlens, const double *numvals,
+    const uint64_t *values, dng_result **out)
+{
+	if (!plan || !out || (npoints && !values))
+		return DNG_EINVAL;
+	dng_result *r = new dng_result();
+	r->init_from_plan(plan);
+	std::vector<std::pair<std::string, uint64_t>> rows;
+	uint64_t total = 0;
+	for (size_t i = 0; i < npoints; i++) {
+		std::string k;
+		for (int j = 0; j < r->ncols; j++) {
+			size_t x = i * r->ncols + j;
+			if (r->col_kind[j] == dng::COL_DISCRETE) {
+				size_t n = strlens[x];
+				k += (char)(n & 0xff);
+				k += (char)((n >> 8) & 0xff);
+				k.append(strs[x], n);
+			} else {
+				double v = numvals[x], o;
+				if (r->col_kind[j] == dng::COL_P2) {
+					int e = 0;
+					if (v != v || std::isinf(v))
+						o = v;
+					else if (v < 1)
+						o = 0;
+					else {
+						std::frexp(v, &e);
+						o = e;
+					}
+				} else {
+					double q = v / r->col_step[j];
+					o = (q != q) ? q : std::floor(q) + 0.0;
+				}
+				uint64_t b;
+				if (o != o)
+					b = 0x7ff8000000000000ull;
+				else
+					memcpy(&b, &o, 8);
+				k += (char)0xFF;
+				k += (char)0xFF;
+				for (int t = 0; t < 8; t++)
+					k += (char)((b >> (8 * t)) & 0xff);
+			}
+		}
+		rows.emplace_back(std::move(k), values[i]);
+		total += values[i];
+	}
+	std::sort(rows.begin(), rows.end());
+	for (auto &kv : rows) {
+		if (!r->keys.empty() && r->keys.back() == kv.first) {
+			r->values.back() += kv.second;
+		} else {
+			r->keys.push_back(kv.first);
+			r->values.push_back(kv.second);
+		}
+	}
+	r->finalize(total);
+	*out = r;
+	return DNG_OK;
+}
 
 int dng_result_dict(const dng_result *cr, const void **buf, size_t *len)
 {

@@ -55,6 +55,7 @@ _SIGS = [
     ('dng_device_count', ctypes.c_int, []),
     ('dng_scan_open', ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_P),
                                      ctypes.c_char_p, ctypes.c_size_t]),
+    ('dng_scan_set_stream', ctypes.c_int, [_P, _P]),
     ('dng_scan_feed', ctypes.c_int, [_P, _P, ctypes.c_size_t]),
     ('dng_scan_feed_pinned', ctypes.c_int, [_P, _P, ctypes.c_size_t]),
     ('dng_scan_feed_device', ctypes.c_int, [_P, _P, ctypes.c_size_t]),
@@ -76,6 +77,10 @@ _SIGS = [
       ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_uint8),
       ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
     ('dng_result_destroy', None, [_P]),
+    ('dng_result_from_points', ctypes.c_int,
+     [_P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_char_p),
+      ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_double),
+      ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(_P)]),
     ('dng_result_dict', ctypes.c_int, [_P, ctypes.POINTER(_P),
                                        ctypes.POINTER(ctypes.c_size_t)]),
     ('dng_dict_union', ctypes.c_int,
@@ -215,6 +220,29 @@ class Result(object):
     __del__ = close
 
 
+def result_from_points(plan, points):
+    """points: [([bytes|float, ...], value)] -> Result (re-aggregated)."""
+    n = len(points)
+    nc = len(points[0][0]) if n else 0
+    m = max(n * nc, 1)
+    strs = (ctypes.c_char_p * m)()
+    lens = (ctypes.c_size_t * m)()
+    nums = (ctypes.c_double * m)()
+    vals = (ctypes.c_uint64 * max(n, 1))()
+    for i, (cols, v) in enumerate(points):
+        vals[i] = v
+        for j, c in enumerate(cols):
+            if isinstance(c, bytes):
+                strs[i * nc + j] = c
+                lens[i * nc + j] = len(c)
+            else:
+                nums[i * nc + j] = c
+    out = _P()
+    _check(lib().dng_result_from_points(plan.handle, n, strs, lens, nums,
+                                        vals, ctypes.byref(out)))
+    return Result(out)
+
+
 def dict_union(dicts):
     n = len(dicts)
     bufs = (ctypes.c_void_p * n)()
@@ -244,6 +272,10 @@ class Scan(object):
                                  ctypes.byref(self.handle), err, len(err))
         if rc != DNG_OK:
             raise DngError(rc, err.value.decode('utf-8', 'replace'))
+
+    def set_stream(self, cuda_stream):
+        _check(lib().dng_scan_set_stream(self.handle, cuda_stream),
+               self.handle)
 
     def feed(self, data):
         b = (ctypes.c_char * len(data)).from_buffer_copy(data) \

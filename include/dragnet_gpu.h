@@ -103,6 +103,11 @@ int dng_device_count(void);
 int dng_scan_open(const dng_plan *plan, int device, dng_scan **out,
     char *err, size_t errlen);
 
+/* Run this scan's kernels on a caller-owned CUDA stream (a cudaStream_t) instead
+ * of the scan's private one, e.g. to bracket them with the caller's events.
+ * Call before the first feed. */
+int dng_scan_set_stream(dng_scan *scan, void *cuda_stream);
+
 /*
  * Feed arbitrary byte chunks (lstream semantics: lines split on '\n', partial
  * trailing line carried to the next feed; lib/format-json.js:32-33).
@@ -152,6 +157,15 @@ void dng_result_destroy(dng_result *r);
 
 /* ---- shard merge (the reference's Manta reduce phase,
  * lib/datasource-manta.js:202-219): sum values over identical tuples ------ */
+
+/* Build a result by re-aggregating skinner points, as the reference's reduce
+ * phase does (`dn scan --points` over json-skinner input,
+ * lib/datasource-manta.js:212-219): string columns are taken as is, numeric
+ * columns are bucket minima and are re-bucketized (idempotent).  Column j of
+ * point i is strs[i*ncols+j] (strlens bytes) or numvals[i*ncols+j]. */
+int dng_result_from_points(const dng_plan *plan, size_t npoints,
+    const char *const *strs, const size_t *strlens, const double *numvals,
+    const uint64_t *values, dng_result **out);
 
 /* Serialised tuple dictionary of a result (keys only), for exchange. */
 int dng_result_dict(const dng_result *r, const void **buf, size_t *len);
