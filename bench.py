@@ -152,14 +152,15 @@ def run_oracle(plan, path, threads, repeat=1):
     return json.loads(out)
 
 
-def sample_file(rows, seed):
-    """A bounded sample of the workload written to tmpfs (host generator:
-    byte-identical to the device generator)."""
+def sample_file(rows, seed, total_rows):
+    """The first `rows` records of the `total_rows`-record workload, written
+    to tmpfs (host generator: byte-identical to the device generator)."""
     from dragnet_b200 import native
     d = '/dev/shm' if os.path.isdir('/dev/shm') else tempfile.gettempdir()
-    path = os.path.join(d, 'dnbench_sample_%d_%d.ndjson' % (seed, rows))
+    path = os.path.join(d, 'dnbench_sample_%d_%d_%d.ndjson' %
+                        (seed, rows, total_rows))
     if not os.path.exists(path):
-        params = native.gen_params(seed=seed, total_records=rows)
+        params = native.gen_params(seed=seed, total_records=total_rows)
         with open(path + '.tmp', 'wb') as f:
             step = 250000
             for first in range(0, rows, step):
@@ -193,7 +194,7 @@ def reference_arm(args, rank, world):
     plan = make_plan(argv, ds)
     threads = os.cpu_count() or 1
     rows = args.cpu_rows
-    path = sample_file(rows, 0xD5A60000)
+    path = sample_file(rows, 0xD5A60000, args.rows)
     for _ in range(max(args.warmup, 1)):
         run_oracle(plan, path, threads)
     secs = []
@@ -397,7 +398,7 @@ def gpu_arm(args, rank, local_rank, world):
     cpu = None
     if world == 1 and args.cpu_rows > 0:
         srows = min(args.cpu_rows, rows)
-        path = sample_file(srows, seed)
+        path = sample_file(srows, seed, rows)
         threads = os.cpu_count() or 1
         doc = run_oracle(plan, path, threads, repeat=2)
         sample = open(path, 'rb').read()

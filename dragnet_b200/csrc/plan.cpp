@@ -13,6 +13,7 @@
 #include "jsnum.cuh"
 #include "../../include/dragnet_gpu.h"
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
@@ -223,6 +224,285 @@ struct JParser {
 		return true;
 	}
 };
+
+/* ---- fast-path automaton ------------------------------------------------- */
+
+struct FastBuilder {
+	FastTab &F;
+	int nstates = 10;	/* FS_* are fixed */
+	int ncls = 0;
+
+	enum { C_OTHER = 0, C_WS, C_NL, C_CTRL, C_QUOTE, C_BSLASH, C_LBRACE,
+	    C_RBRACE, C_LBRACK, C_RBRACK, C_COLON, C_COMMA, C_MINUS, C_PLUS,
+	    C_DOT, C_ZERO, C_DIGIT, C_a, C_b, C_cd, C_e, C_f, C_l, C_n, C_r, C_s,
+	    C_t, C_u, C_AF, C_E, C_SLASH, C_WSC, C_BASE_COUNT };
+
+	explicit FastBuilder(FastTab &f) : F(f) {}
+
+	int alloc() { return nstates < FAST_MAXSTATES ? nstates++ : -1; }
+	void set(int st, int cls, int next, int flags = 0) {
+		F.trans[st * FAST_NCLS + cls] = (u16)(next | (flags << 8));
+	}
+	void set_all(int st, int next) {
+		for (int c = 0; c < FAST_NCLS; c++)
+			set(st, c, next);
+	}
+	static int base_class(int b) {
+		if (b == ' ') return C_WS;
+		if (b == '\t' || b == '\r') return C_WSC;	/* ws, but not inside strings */
+		if (b == '\n') return C_NL;
+		if (b < 0x20) return C_CTRL;
+		switch (b) {
+		case '"': return C_QUOTE; case '\\': return C_BSLASH;
+		case '{': return C_LBRACE; case '}': return C_RBRACE;
+		case '[': return C_LBRACK; case ']': return C_RBRACK;
+		case ':': return C_COLON; case ',': return C_COMMA;
+		case '-': return C_MINUS; case '+': return C_PLUS;
+		case '.': return C_DOT; case '0': return C_ZERO;
+		case 'a': return C_a; case 'b': return C_b;
+		case 'c': case 'd': return C_cd;
+		case 'e': return C_e; case 'f': return C_f; case 'l': return C_l;
+		case 'n': return C_n; case 'r': return C_r; case 's': return C_s;
+		case 't': return C_t; case 'u': return C_u;
+		case 'A': case 'B': case 'C': case 'D': case 'F': return C_AF;
+		case 'E': return C_E; case '/': return C_SLASH;
+		}
+		if (b >= '1' && b <= '9') return C_DIGIT;
+		return C_OTHER;
+	}
+
+	bool build(const std::vector<std::string> &keys,
+	    const std::vector<std::vector<int>> &key_term,	/* [ctx][key] */
+	    const std::vector<std::vector<int>> &key_child) {
+		memset(&F, 0, sizeof (F));
+		if (keys.size() > FAST_MAXKEYS)
+			return false;
+		/* classes: base classes, then one per distinct key byte */
+		int base_of[FAST_NCLS];
+		for (int c = 0; c < C_BASE_COUNT; c++)
+			base_of[c] = c;
+		ncls = C_BASE_COUNT;
+		for (int b = 0; b < 256; b++)
+			F.cls[b] = (u8)base_class(b);
+		for (auto &k : keys) {
+			for (unsigned char b : k) {
+				if (b < 0x20 || b == '"' || b == '\\')
+					continue;	/* only reachable escaped */
+				if (F.cls[b] >= C_BASE_COUNT)
+					continue;
+				if (ncls >= FAST_NCLS)
+					return false;
+				base_of[ncls] = F.cls[b];
+				F.cls[b] = (u8)ncls++;
+			}
+		}
+		/* states */
+		int OKs = alloc(), V[2] = { alloc(), alloc() };	/* V_O, V_A */
+		int S[2], SE[2], SU[2][4], NM[2], N0[2], NI[2], ND[2], NF[2],
+		    NE[2], NS[2], NX[2], T[2][3], Fs[2][4], L[2][3];
+		for (int x = 0; x < 2; x++) {
+			S[x] = alloc(); SE[x] = alloc();
+			for (int i = 0; i < 4; i++) SU[x][i] = alloc();
+			NM[x] = alloc(); N0[x] = alloc(); NI[x] = alloc();
+			ND[x] = alloc(); NF[x] = alloc(); NE[x] = alloc();
+			NS[x] = alloc(); NX[x] = alloc();
+			for (int i = 0; i < 3; i++) T[x][i] = alloc();
+			for (int i = 0; i < 4; i++) Fs[x][i] = alloc();
+			for (int i = 0; i < 3; i++) L[x][i] = alloc();
+		}
+		int KX = alloc();
+		/* trie over the candidate keys */
+		struct Node { std::map<int, int> kids; int key = -1; int st; };
+		std::vector<Node> trie(1);
+		trie[0].st = alloc();
+		for (size_t g = 0; g < keys.size(); g++) {
+			bool reachable = true;
+			for (unsigned char b : keys[g])
+				if (b < 0x20 || b == '"' || b == '\\')
+					reachable = false;
+			if (!reachable)
+				continue;
+			int t = 0;
+			for (unsigned char b : keys[g]) {
+				auto it = trie[t].kids.find(b);
+				if (it == trie[t].kids.end()) {
+					Node n;
+					n.st = alloc();
+					if (n.st < 0)
+						return false;
+					trie.push_back(n);
+					trie[t].kids[b] = (int)trie.size() - 1;
+					t = (int)trie.size() - 1;
+				} else {
+					t = it->second;
+				}
+			}
+			trie[t].key = (int)g;
+		}
+		if (nstates + (int)keys.size() > 250 || KX < 0 ||
+		    trie[0].st < 0)
+			return false;
+		F.kc_base = (u8)nstates;	/* ids only, no rows */
+		F.nstates = (u8)nstates;
+		F.nkeys = (u8)keys.size();
+
+		for (int st = 0; st < nstates; st++)
+			set_all(st, FS_ERR);
+		set_all(FS_FIN, FS_FIN);
+		set_all(FS_FB, FS_FB);
+		/* START: only containers take the fast path */
+		set_all(FS_START, FS_FB);
+		set(FS_START, C_WS, FS_START);
+		set(FS_START, C_NL, FS_ERR);
+		set(FS_START, C_LBRACE, FS_OF, FE_PUSH | FE_OBJ);
+		set(FS_START, C_LBRACK, FS_AF, FE_PUSH);
+		set(FS_DONE, C_WS, FS_DONE);
+		set(FS_DONE, C_NL, FS_FIN);
+		/* keys */
+		set(FS_OF, C_WS, FS_OF);
+		set(FS_OF, C_QUOTE, trie[0].st);
+		set(FS_OF, C_RBRACE, FS_AFTER_O, FE_POP | FE_OBJ);
+		set(OKs, C_WS, OKs);
+		set(OKs, C_QUOTE, trie[0].st);
+		auto key_row = [&](int st) {
+			for (int c = 0; c < ncls; c++)
+				set(st, c, KX);
+			set(st, C_CTRL, FS_ERR);
+			set(st, C_NL, FS_ERR);
+			set(st, C_BSLASH, FS_FB);
+			set(st, C_QUOTE, FS_KC);
+		};
+		key_row(KX);
+		for (auto &n : trie) {
+			key_row(n.st);
+			for (auto &kv : n.kids)
+				set(n.st, F.cls[kv.first], trie[kv.second].st);
+			if (n.key >= 0)
+				set(n.st, C_QUOTE, F.kc_base + n.key, FE_KEYHIT);
+		}
+		set(FS_KC, C_WS, FS_KC);
+		set(FS_KC, C_COLON, V[0]);
+		/* values */
+		for (int x = 0; x < 2; x++) {
+			int after = x == 0 ? FS_AFTER_O : FS_AFTER_A;
+			int rows[2] = { V[x], x == 1 ? FS_AF : -1 };
+			for (int ri = 0; ri < 2; ri++) {
+				int st = rows[ri];
+				if (st < 0)
+					continue;
+				set(st, C_WS, st);
+				set(st, C_QUOTE, S[x], FE_VALSTART);
+				set(st, C_LBRACE, FS_OF, FE_PUSH | FE_OBJ);
+				set(st, C_LBRACK, FS_AF, FE_PUSH);
+				set(st, C_MINUS, NM[x], FE_VALSTART);
+				set(st, C_ZERO, N0[x], FE_VALSTART);
+				set(st, C_DIGIT, NI[x], FE_VALSTART);
+				set(st, C_t, T[x][0], FE_VALSTART);
+				set(st, C_f, Fs[x][0], FE_VALSTART);
+				set(st, C_n, L[x][0], FE_VALSTART);
+			}
+			/* strings */
+			for (int c = 0; c < ncls; c++)
+				set(S[x], c, S[x]);
+			set(S[x], C_CTRL, FS_ERR);
+			set(S[x], C_NL, FS_ERR);
+			set(S[x], C_BSLASH, SE[x]);
+			set(S[x], C_QUOTE, after, FE_VALEND_INCL);
+			const int esc[] = { C_QUOTE, C_BSLASH, C_SLASH, C_b, C_f, C_n,
+			    C_r, C_t };
+			for (int c : esc)
+				set(SE[x], c, S[x]);
+			set(SE[x], C_u, SU[x][0]);
+			const int hex[] = { C_ZERO, C_DIGIT, C_a, C_b, C_cd, C_e, C_f,
+			    C_AF, C_E };
+			for (int i = 0; i < 4; i++)
+				for (int c : hex)
+					set(SU[x][i], c, i == 3 ? S[x] : SU[x][i + 1]);
+			/* numbers */
+			set(NM[x], C_ZERO, N0[x]);
+			set(NM[x], C_DIGIT, NI[x]);
+			auto term = [&](int st) {
+				set(st, C_WS, after, FE_VALEND_EXCL);
+				set(st, C_COMMA, x == 0 ? OKs : V[1], FE_VALEND_EXCL);
+				if (x == 0)
+					set(st, C_RBRACE, FS_AFTER_O,
+					    FE_POP | FE_OBJ | FE_VALEND_EXCL);
+				else
+					set(st, C_RBRACK, FS_AFTER_O,
+					    FE_POP | FE_VALEND_EXCL);
+			};
+			set(N0[x], C_DOT, ND[x]);
+			set(N0[x], C_e, NE[x]); set(N0[x], C_E, NE[x]);
+			term(N0[x]);
+			set(NI[x], C_ZERO, NI[x]); set(NI[x], C_DIGIT, NI[x]);
+			set(NI[x], C_DOT, ND[x]);
+			set(NI[x], C_e, NE[x]); set(NI[x], C_E, NE[x]);
+			term(NI[x]);
+			set(ND[x], C_ZERO, NF[x]); set(ND[x], C_DIGIT, NF[x]);
+			set(NF[x], C_ZERO, NF[x]); set(NF[x], C_DIGIT, NF[x]);
+			set(NF[x], C_e, NE[x]); set(NF[x], C_E, NE[x]);
+			term(NF[x]);
+			set(NE[x], C_PLUS, NS[x]); set(NE[x], C_MINUS, NS[x]);
+			set(NE[x], C_ZERO, NX[x]); set(NE[x], C_DIGIT, NX[x]);
+			set(NS[x], C_ZERO, NX[x]); set(NS[x], C_DIGIT, NX[x]);
+			set(NX[x], C_ZERO, NX[x]); set(NX[x], C_DIGIT, NX[x]);
+			term(NX[x]);
+			/* literals */
+			set(T[x][0], C_r, T[x][1]); set(T[x][1], C_u, T[x][2]);
+			set(T[x][2], C_e, after, FE_VALEND_INCL);
+			set(Fs[x][0], C_a, Fs[x][1]); set(Fs[x][1], C_l, Fs[x][2]);
+			set(Fs[x][2], C_s, Fs[x][3]);
+			set(Fs[x][3], C_e, after, FE_VALEND_INCL);
+			set(L[x][0], C_u, L[x][1]); set(L[x][1], C_l, L[x][2]);
+			set(L[x][2], C_l, after, FE_VALEND_INCL);
+		}
+		set(FS_AF, C_RBRACK, FS_AFTER_O, FE_POP);
+		set(FS_AFTER_O, C_WS, FS_AFTER_O);
+		set(FS_AFTER_O, C_COMMA, OKs);
+		set(FS_AFTER_O, C_RBRACE, FS_AFTER_O, FE_POP | FE_OBJ);
+		set(FS_AFTER_A, C_WS, FS_AFTER_A);
+		set(FS_AFTER_A, C_COMMA, V[1]);
+		set(FS_AFTER_A, C_RBRACK, FS_AFTER_O, FE_POP);
+		/* tab and CR are whitespace between tokens but control
+		 * characters inside strings and keys */
+		for (int st = 0; st < nstates; st++)
+			F.trans[st * FAST_NCLS + C_WSC] =
+			    F.trans[st * FAST_NCLS + C_WS];
+		for (int x = 0; x < 2; x++)
+			set(S[x], C_WSC, FS_ERR);
+		set(KX, C_WSC, FS_ERR);
+		for (auto &n : trie)
+			set(n.st, C_WSC, FS_ERR);
+		/* own classes of key bytes behave like their base class wherever
+		 * the trie did not claim them */
+		for (int c = C_BASE_COUNT; c < ncls; c++) {
+			for (int st = 0; st < nstates; st++) {
+				bool trie_edge = false;
+				for (auto &n : trie)
+					if (n.st == st)
+						for (auto &kv : n.kids)
+							if (F.cls[kv.first] == c)
+								trie_edge = true;
+				if (!trie_edge)
+					F.trans[st * FAST_NCLS + c] =
+					    F.trans[st * FAST_NCLS + base_of[c]];
+			}
+		}
+		/* candidate map */
+		memset(F.candmap, 0xFF, sizeof (F.candmap));
+		for (size_t c = 0; c < key_term.size(); c++) {
+			for (size_t g = 0; g < keys.size(); g++) {
+				F.candmap[c * FAST_MAXKEYS + g][0] =
+				    (u8)key_term[c][g];
+				F.candmap[c * FAST_MAXKEYS + g][1] =
+				    (u8)key_child[c][g];
+			}
+		}
+		F.ok = 1;
+		return true;
+	}
+};
+
 
 /* ---- compiler --------------------------------------------------------- */
 
@@ -668,9 +948,39 @@ struct Compiler {
 			P.path[i].slot0 = (u8)paths[pathinfo[i].first].slot0;
 			P.path[i].nlevels = (u8)pathinfo[i].second;
 		}
+		/* fast-path automaton (optional: plans it cannot express simply
+		 * keep using the general parser) */
+		{
+			std::vector<std::string> keys;
+			bool arraylike = false;
+			for (size_t c = 0; c < ctx_cands.size(); c++) {
+				if (P.ctx[c].arraylike)
+					arraylike = true;
+				for (auto &cr : ctx_cands[c])
+					if (std::find(keys.begin(), keys.end(),
+					    cr.key) == keys.end())
+						keys.push_back(cr.key);
+			}
+			std::vector<std::vector<int>> kt(ctx_cands.size()),
+			    kc(ctx_cands.size());
+			for (size_t c = 0; c < ctx_cands.size(); c++) {
+				kt[c].assign(keys.size(), -1);
+				kc[c].assign(keys.size(), -1);
+				for (auto &cr : ctx_cands[c]) {
+					size_t g = std::find(keys.begin(),
+					    keys.end(), cr.key) - keys.begin();
+					kt[c][g] = cr.term_slot;
+					kc[c][g] = cr.child_ctx;
+				}
+			}
+			FastBuilder fb(P.fast);
+			if (arraylike || !fb.build(keys, kt, kc))
+				P.fast.ok = 0;
+		}
 		return this->code == DNG_OK;
 	}
 };
+
 
 } /* namespace */
 

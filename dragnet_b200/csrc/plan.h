@@ -99,6 +99,38 @@ struct Col {
 enum : u8 { COL_DISCRETE = 0, COL_P2 = 1, COL_LINEAR = 2 };
 enum : u8 { FMT_JSON = 0, FMT_SKINNER = 1 };
 
+/*
+ * Fast path: a per-plan byte automaton (record.cuh fast_step).  Every lane of
+ * a warp feeds one byte of its own record per iteration through
+ *     cls = fast.cls[byte];  e = fast.trans[state * FAST_NCLS + cls]
+ * (low byte = next state, high byte = event flags), so the warp stays in
+ * lock step; the plan's candidate keys are folded into the automaton as a
+ * trie, so "is this key one we need" costs nothing per byte.  Only flagged
+ * bytes (container open/close, a candidate key, the value after one) run
+ * divergent code.  Anything the automaton does not model exactly (escapes in
+ * keys, nesting > 31, a top-level scalar) ends in FS_FB and the record is
+ * re-parsed by the general parser (parse_record).
+ */
+enum : int { FAST_NCLS = 64, FAST_MAXSTATES = 128, FAST_MAXKEYS = 48 };
+enum : u8 {			/* event flags (high byte of a transition) */
+	FE_PUSH = 1, FE_POP = 2, FE_OBJ = 4, FE_KEYHIT = 8,
+	FE_VALSTART = 16, FE_VALEND_INCL = 32, FE_VALEND_EXCL = 64
+};
+enum : u8 {			/* fixed state numbers */
+	FS_ERR = 0, FS_FIN = 1, FS_FB = 2, FS_START = 3, FS_DONE = 4,
+	FS_AFTER_O = 5, FS_AFTER_A = 6, FS_OF = 7, FS_AF = 8, FS_KC = 9
+};
+
+struct FastTab {
+	u16 trans[FAST_MAXSTATES * FAST_NCLS];
+	u8 cls[256];
+	u8 candmap[MAX_CTX * FAST_MAXKEYS][2];	/* [ctx][key] -> term, child */
+	u8 ok;			/* tables are valid for this plan */
+	u8 nstates, nkeys;
+	u8 kc_base;		/* state kc_base + g = "key g just closed" */
+	u8 pad[4];
+};
+
 struct DevPlan {
 	Leaf code[MAX_CODE];
 	Col col[MAX_COLS];
@@ -113,6 +145,7 @@ struct DevPlan {
 	int8_t sk_fields_slot, sk_value_slot;	/* json-skinner envelope */
 	u8 pad[3];
 	char pool[POOL_BYTES];
+	FastTab fast;
 };
 
 } /* namespace dng */

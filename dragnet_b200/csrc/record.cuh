@@ -516,6 +516,147 @@ invalid:
 	R.flags = flags | RF_INVALID;
 }
 
+/* ---- fast path: lock-step byte automaton (plan.h FastTab) ----------------- */
+
+struct FastState {
+	u32 state, depth, types, arm, vstart, set_mask;
+	int ctx, ctx_depth, pend_term, pend_child;
+};
+
+DNG_HD void fast_init(FastState &s)
+{
+	s.state = FS_START;
+	s.depth = 0;
+	s.types = 0;
+	s.arm = FE_PUSH | FE_POP | FE_KEYHIT;
+	s.vstart = 0;
+	s.set_mask = 0;
+	s.ctx = -1;
+	s.ctx_depth = 0;
+	s.pend_term = -1;
+	s.pend_child = -1;
+}
+
+/* the divergent part: runs only on bytes whose transition carries an armed
+ * event flag (container open/close, a candidate key, the value after one) */
+DNG_HD void fast_event(FastState &s, const DevPlan &P, u64 *slots, u32 f,
+    u32 pos)
+{
+	const u32 VAL = FE_VALSTART | FE_VALEND_INCL | FE_VALEND_EXCL;
+	if (f & s.arm & FE_VALSTART)
+		s.vstart = pos;
+	if (f & s.arm & (FE_VALEND_INCL | FE_VALEND_EXCL)) {
+		u32 end = pos + ((f & FE_VALEND_INCL) ? 1u : 0u);
+		if (s.pend_term >= 0) {
+			slots[s.pend_term] = (u64)s.vstart | ((u64)end << 32);
+			s.set_mask |= 1u << s.pend_term;
+		}
+		if (s.pend_child >= 0)
+			s.set_mask &= ~P.ctx[s.pend_child].subtree_mask;
+		s.pend_term = -1;
+		s.pend_child = -1;
+		s.arm &= ~VAL;
+	}
+	if (f & FE_KEYHIT) {
+		u32 g = s.state - P.fast.kc_base;
+		s.state = FS_KC;
+		if ((int)s.depth == s.ctx_depth && s.ctx >= 0) {
+			const u8 *cm = P.fast.candmap[s.ctx * FAST_MAXKEYS + g];
+			if (cm[0] != 0xFF || cm[1] != 0xFF) {
+				s.pend_term = (int8_t)cm[0];
+				s.pend_child = (int8_t)cm[1];
+				s.arm |= VAL;
+			}
+		}
+	}
+	if (f & FE_PUSH) {
+		u32 isobj = (f & FE_OBJ) ? 1u : 0u;
+		if (s.depth >= 31)
+			s.state = FS_FB;
+		if (s.pend_term >= 0) {
+			slots[s.pend_term] = (u64)pos;	/* end 0: container */
+			s.set_mask |= 1u << s.pend_term;
+		}
+		int enter = -1;
+		if (s.pend_child >= 0) {
+			s.set_mask &= ~P.ctx[s.pend_child].subtree_mask;
+			enter = s.pend_child;
+		} else if (s.depth == 0 && P.nctx) {
+			enter = 0;
+		}
+		if (enter >= 0 && isobj) {
+			s.ctx = enter;
+			s.ctx_depth = (int)s.depth + 1;
+		}
+		s.pend_term = -1;
+		s.pend_child = -1;
+		s.arm &= ~VAL;
+		s.depth = (s.depth + 1) & 31;
+		s.types = (s.types & ~(1u << s.depth)) | (isobj << s.depth);
+	}
+	if (f & FE_POP) {
+		if ((int)s.depth == s.ctx_depth && s.ctx >= 0) {
+			s.ctx = P.ctx[s.ctx].parent;
+			s.ctx_depth--;
+		}
+		s.depth = (s.depth - 1) & 31;
+		s.state = s.depth == 0 ? (u32)FS_DONE :
+		    ((s.types >> s.depth) & 1) ? (u32)FS_AFTER_O : (u32)FS_AFTER_A;
+	}
+}
+
+DNG_HD void fast_step(FastState &s, const DevPlan &P, u64 *slots, u32 c, u32 pos)
+{
+	u32 e = P.fast.trans[s.state * FAST_NCLS + P.fast.cls[c]];
+	s.state = e & 0xff;
+	u32 f = e >> 8;
+	if (f & s.arm)
+		fast_event(s, P, slots, f, pos);
+}
+
+/* turn the (start, end) spans the automaton captured into packed values */
+DNG_HD void fast_finish(const u8 *rec, const FastState &s, RecState &R)
+{
+	R.set_mask = s.set_mask;
+	R.flags = 0;
+	u32 m = s.set_mask;
+	while (m) {
+		u32 slot = 0;
+		while (!((m >> slot) & 1))
+			slot++;
+		m &= m - 1;
+		u32 start = (u32)R.slots[slot], end = (u32)(R.slots[slot] >> 32);
+		u32 c0 = rec[start];
+		u64 v;
+		if (end == 0) {
+			v = mkval(c0 == '{' ? T_OBJ : T_ARR, start, 0, 0);
+		} else if (c0 == '"') {
+			u32 esc = 0;
+			for (u32 i = start + 1; i + 1 < end; i++)
+				if (rec[i] == '\\')
+					esc = VF_ESCAPED;
+			v = mkval(T_STR, start + 1, end - start - 2, esc);
+		} else if (c0 == 't') {
+			v = mkval(T_TRUE, start, 4, 0);
+		} else if (c0 == 'f') {
+			v = mkval(T_FALSE, start, 5, 0);
+		} else if (c0 == 'n') {
+			v = mkval(T_NULL, start, 4, 0);
+		} else {
+			u32 neg = c0 == '-', simple = VF_SIMPLEINT;
+			u32 nlen = end - start;
+			for (u32 i = start + neg; i < end; i++)
+				if (rec[i] < '0' || rec[i] > '9')
+					simple = 0;
+			if (nlen - neg > 15 ||
+			    (neg && nlen == 2 && rec[start + 1] == '0'))
+				simple = 0;
+			v = mkval(T_NUM, start, nlen, simple);
+		}
+		R.slots[slot] = v;
+	}
+}
+
 /* ---- values ------------------------------------------------------------ */
 
 struct V {

@@ -39,8 +39,9 @@ namespace dng {
 #define DNG_PRELAP 4096			/* bytes staged before the tile */
 #endif
 #define DNG_CTAS_PER_SM 2
-#define DNG_NLCAP 2048			/* newline positions per pass */
-#define DNG_SSLOTS 256			/* shared hash table slots */
+#define DNG_NLCAP 1024			/* newline positions per pass */
+#define DNG_SSLOTS 128			/* shared hash table slots */
+#define DNG_FASTMAX 1024		/* longest line the lock-step automaton takes */
 #define DNG_SKEY 40			/* inline key bytes per shared slot */
 #define DNG_MAXREC (1u << 24)		/* longest line handled */
 
@@ -93,7 +94,9 @@ struct ScanArgs {
 static constexpr size_t SMEM_PLAN = (sizeof (DevPlan) + 127) & ~(size_t)127;
 static constexpr size_t SMEM_TAB = sizeof (SSlot) * DNG_SSLOTS;
 static constexpr size_t SMEM_NL = sizeof (u32) * DNG_NLCAP;
-static constexpr size_t SMEM_DATA = DNG_PRELAP + DNG_TILE + 128;
+/* the slack lets lanes of a warp keep stepping (in an absorbing state) past
+ * the end of their own short record while a neighbour finishes a longer one */
+static constexpr size_t SMEM_DATA = DNG_PRELAP + DNG_TILE + DNG_FASTMAX + 128;
 static constexpr size_t SMEM_TOTAL = SMEM_PLAN + SMEM_TAB + SMEM_NL + SMEM_DATA;
 
 /* ---- global table ------------------------------------------------------- */
@@ -252,11 +255,25 @@ __device__ __forceinline__ u32 nl_mask(u32 w)
 
 /* ---- one record ----------------------------------------------------------- */
 
+/* stages after JSON decode + aggregation, for a parsed record */
+__device__ __forceinline__ void scan_tail(const u8 *rec, u32 len,
+    const DevPlan &P, RecState &R, SSlot *stab, const GTable &gt,
+    LocalCounters &C)
+{
+	u8 kbuf[KEY_MAX + 16];
+	u32 klen;
+	u64 w;
+	if (process_record(rec, len, P, R, C, kbuf, klen, w)) {
+		u64 h = key_hash(kbuf, klen);
+		shared_add(stab, gt, h, kbuf, klen, w);
+	}
+}
+
+/* general (branchy, exact for everything) path */
 __device__ __forceinline__ void scan_one(const u8 *rec, u32 len,
     const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C)
 {
 	RecState R;
-	u8 kbuf[KEY_MAX + 16];
 	C.lines++;
 	if (len >= DNG_MAXREC) {
 		C.unsupported++;
@@ -269,12 +286,13 @@ __device__ __forceinline__ void scan_one(const u8 *rec, u32 len,
 		C.invalid_json++;
 		return;
 	}
-	u32 klen;
-	u64 w;
-	if (process_record(rec, len, P, R, C, kbuf, klen, w)) {
-		u64 h = key_hash(kbuf, klen);
-		shared_add(stab, gt, h, kbuf, klen, w);
-	}
+	scan_tail(rec, len, P, R, stab, gt, C);
+}
+
+__device__ __noinline__ void scan_one_shared(const u8 *rec, u32 len,
+    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C)
+{
+	scan_one(rec, len, P, stab, gt, C);
 }
 
 /* out-of-line copy for lines that begin before the staged window (rare):
@@ -428,29 +446,61 @@ scan_kernel(const ScanArgs a)
 			u32 n = total - pass;
 			if (n > DNG_NLCAP)
 				n = DNG_NLCAP;
-			for (u32 r = tid; r < n; r += DNG_NT) {
-				u32 end = nlpos[r];
-				u32 beg;
+			for (u32 rb = 0; rb < n; rb += DNG_NT) {
+				const u32 r = rb + tid;
+				const bool have = r < n;
+				u32 end = 0, beg = 0;
 				bool islong = false;
-				if (r > 0) {
-					beg = nlpos[r - 1] + 1;
-				} else if (pass > 0) {
-					beg = s_prev + 1;
-				} else {
-					u32 p = off0 < lower ? lower : off0;
-					if (p > end)
-						p = end;
-					while (p > lower && sdata[p - 1] != '\n')
-						p--;
-					beg = p;
-					if (p == lower && ws + lower > a.start &&
-					    (p == 0 || sdata[p - 1] != '\n'))
-						islong = true;
+				if (have) {
+					end = nlpos[r];
+					if (r > 0) {
+						beg = nlpos[r - 1] + 1;
+					} else if (pass > 0) {
+						beg = s_prev + 1;
+					} else {
+						u32 p = off0 < lower ? lower : off0;
+						if (p > end)
+							p = end;
+						while (p > lower &&
+						    sdata[p - 1] != '\n')
+							p--;
+						beg = p;
+						if (p == lower && ws + lower > a.start &&
+						    (p == 0 || sdata[p - 1] != '\n'))
+							islong = true;
+					}
 				}
-				if (!islong) {
-					scan_one(sdata + beg, end - beg, P, stab,
+				const u32 len = end - beg;
+				/*
+				 * Lock-step fast path: every lane steps the plan's
+				 * byte automaton over its own record; lanes without
+				 * a (short, newline-terminated) record idle in the
+				 * absorbing FIN state.
+				 */
+				const bool fast = have && !islong && P.fast.ok &&
+				    len <= DNG_FASTMAX && end < wlen;
+				RecState R;
+				FastState fs;
+				fast_init(fs);
+				if (!fast)
+					fs.state = FS_FIN;
+				const u8 *rec = sdata + (fast ? beg : 0);
+				u32 trip = __reduce_max_sync(0xffffffffu,
+				    fast ? len + 1 : 0);
+#pragma unroll 4
+				for (u32 i = 0; i < trip; i++)
+					fast_step(fs, P, R.slots, rec[i], i);
+				if (fast && fs.state == FS_FIN) {
+					C.lines++;
+					fast_finish(rec, fs, R);
+					scan_tail(rec, len, P, R, stab, a.tab, C);
+				} else if (fast && fs.state == FS_ERR) {
+					C.lines++;
+					C.invalid_json++;
+				} else if (have && !islong) {
+					scan_one_shared(sdata + beg, len, P, stab,
 					    a.tab, C);
-				} else {
+				} else if (have) {
 					/* the line began before the staged
 					 * window: find its start in HBM and
 					 * parse it from there */

@@ -50,6 +50,8 @@ int main(int argc, char **argv)
 
 	LocalCounters C;
 	memset(&C, 0, sizeof (C));
+	bool use_fast = getenv("DNG_HOSTCHECK_FAST") != nullptr;
+	unsigned long nfast = 0;
 	std::map<std::string, uint64_t> table;
 	uint64_t total = 0;
 	static RecState R;
@@ -61,7 +63,30 @@ int main(int argc, char **argv)
 		u32 len = (u32)(end - pos);
 		const u8 *rec = (const u8 *)data.data() + pos;
 		C.lines++;
-		parse_record(rec, len, plan.dev, R);
+		bool done = false;
+		if (use_fast && plan.dev.fast.ok && len <= 2048) {
+			FastState fs;
+			fast_init(fs);
+			for (u32 i = 0; i <= len; i++)
+				fast_step(fs, plan.dev, R.slots,
+				    i < len ? rec[i] : (u8)'\n', i);
+			/* keep stepping on garbage like neighbouring lanes do */
+			for (u32 i = 0; i < 64; i++)
+				fast_step(fs, plan.dev, R.slots,
+				    (u8)("{\"x\":[1,\"\\\n}]"[i % 12]), len + 1 + i);
+			if (fs.state == FS_FIN) {
+				fast_finish(rec, fs, R);
+				done = true;
+				nfast++;
+			} else if (fs.state == FS_ERR) {
+				R.flags = RF_INVALID;
+				R.set_mask = 0;
+				done = true;
+				nfast++;
+			}
+		}
+		if (!done)
+			parse_record(rec, len, plan.dev, R);
 		if (R.flags & RF_UNSUPPORTED)
 			C.unsupported++;
 		if (R.flags & RF_INVALID) {
@@ -112,6 +137,6 @@ int main(int argc, char **argv)
 	CTR(ds_failedeval); CTR(user_filtered); CTR(user_failedeval);
 	CTR(synth_undef); CTR(synth_baddate); CTR(time_filtered);
 	CTR(time_failedeval); CTR(aggr); CTR(slow);
-	printf("\"unsupported\":%u}}\n", C.unsupported);
+	printf("\"unsupported\":%u},\"nfast\":%lu}\n", C.unsupported, nfast);
 	return 0;
 }

@@ -7,6 +7,16 @@ import sys
 
 import pytest
 
+
+@pytest.fixture(params=['general', 'fast'], autouse=True)
+def parser_mode(request, monkeypatch):
+    """Run every case with the general parser only, and with the lock-step
+    fast automaton (+ fallback) the kernel uses."""
+    if request.param == 'fast':
+        monkeypatch.setenv('DNG_HOSTCHECK_FAST', '1')
+    else:
+        monkeypatch.delenv('DNG_HOSTCHECK_FAST', raising=False)
+
 sys.path.insert(0, os.path.dirname(__file__))
 import corpus  # noqa: E402
 from engines import canon_points, hostcheck_engine, py_engine  # noqa: E402
