@@ -33,7 +33,10 @@ namespace dng {
 #define DNG_NT 256			/* threads per CTA */
 #endif
 #ifndef DNG_TILE
-#define DNG_TILE 49152			/* bytes of input a tile owns */
+/* bytes of input a tile owns: DNG_NT slices of 13 x 16 bytes -- an odd number
+ * of 16-byte units per lane keeps the per-lane uint4 reads of the newline
+ * index free of shared-memory bank conflicts */
+#define DNG_TILE (DNG_NT * 208)
 #endif
 #ifndef DNG_PRELAP
 #define DNG_PRELAP 4096			/* bytes staged before the tile */
@@ -253,6 +256,17 @@ __device__ __forceinline__ u32 nl_mask(u32 w)
 	return ~(t | 0x7f7f7f7fu);
 }
 
+/* 0x80 in byte k of the result iff lo <= p + k < hi (p = address of byte 0) */
+__device__ __forceinline__ u32 byte_range_mask(u32 p, u32 lo, u32 hi)
+{
+	u32 m = 0;
+#pragma unroll
+	for (u32 k = 0; k < 4; k++)
+		if (p + k >= lo && p + k < hi)
+			m |= 0x80u << (8 * k);
+	return m;
+}
+
 /* ---- one record ----------------------------------------------------------- */
 
 /* stages after JSON decode + aggregation, for a parsed record */
@@ -382,16 +396,13 @@ scan_kernel(const ScanArgs a)
 			u32 m0 = nl_mask(v.x), m1 = nl_mask(v.y);
 			u32 m2 = nl_mask(v.z), m3 = nl_mask(v.w);
 			if (p + 16 > c1 || p < lower) {
-				/* partial word: count byte by byte */
-				u32 e = c1 - p < 16 ? c1 - p : 16;
-				for (u32 k = 0; k < e; k++)
-					if (p + k >= lower &&
-					    sdata[p + k] == '\n')
-						cnt++;
-			} else {
-				cnt += __popc(m0) + __popc(m1) + __popc(m2) +
-				    __popc(m3);
+				/* partial word: keep only bytes in [lower, c1) */
+				m0 &= byte_range_mask(p, lower, c1);
+				m1 &= byte_range_mask(p + 4, lower, c1);
+				m2 &= byte_range_mask(p + 8, lower, c1);
+				m3 &= byte_range_mask(p + 12, lower, c1);
 			}
+			cnt += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
 		}
 		/* an unterminated final line ends at a virtual newline */
 		const bool vnl = a.final && we == a.nbytes && tid == DNG_NT - 1 &&
@@ -431,12 +442,23 @@ scan_kernel(const ScanArgs a)
 			/* write this pass's newline positions, in order */
 			u32 idx = mybase;
 			if (idx < pass + DNG_NLCAP && idx + cnt > pass) {
-				for (u32 p = c0; p < c1; p++) {
-					if (p >= lower && sdata[p] == '\n') {
-						if (idx >= pass &&
-						    idx < pass + DNG_NLCAP)
-							nlpos[idx - pass] = p;
-						idx++;
+				for (u32 p = c0; p < c1; p += 16) {
+					uint4 v = *(const uint4 *)(sdata + p);
+					u32 mm[4] = { nl_mask(v.x), nl_mask(v.y),
+					    nl_mask(v.z), nl_mask(v.w) };
+#pragma unroll
+					for (u32 q = 0; q < 4; q++) {
+						u32 m = mm[q] & byte_range_mask(
+						    p + 4 * q, lower, c1);
+						while (m) {
+							u32 b = (__ffs(m) - 1) >> 3;
+							m &= m - 1;
+							if (idx >= pass &&
+							    idx < pass + DNG_NLCAP)
+								nlpos[idx - pass] =
+								    p + 4 * q + b;
+							idx++;
+						}
 					}
 				}
 				if (vnl && idx >= pass && idx < pass + DNG_NLCAP)
