@@ -387,6 +387,22 @@ def gpu_arm(args, rank, local_rank, world):
                                    for c in cols)
                            for cols, _ in E['last'][0])
 
+    # ---- N > 1: the merged tallies must equal the sum of the per-rank ones ----
+    merge_parity = None
+    if world > 1:
+        local = one_scan(feed_resident, merge=False)[0]
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(local, gathered, dst=0)
+        if rank == 0:
+            acc = {}
+            for pts in gathered:
+                for cols, v in pts:
+                    k = tuple(repr(c) for c in cols)
+                    acc[k] = acc.get(k, 0) + v
+            got = {tuple(repr(c) for c in cols): v
+                   for cols, v in R['last'][0]}
+            merge_parity = 'exact' if got == acc else 'MISMATCH'
+
     if rank != 0:
         if comm is not None:
             L.dng_comm_destroy(comm)
@@ -456,6 +472,7 @@ def gpu_arm(args, rank, local_rank, world):
         'gpu_launches': R['launches'],
         'clocks': R['clocks'],
         'parity': parity,
+        'merge_parity': merge_parity,
     }
     if cpu:
         line['cpu_baseline'] = cpu
