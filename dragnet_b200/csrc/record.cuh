@@ -571,37 +571,43 @@ DNG_HD void fast_event(FastState &s, const DevPlan &P, u64 *slots, u32 f,
 	}
 	if (f & FE_PUSH) {
 		u32 isobj = (f & FE_OBJ) ? 1u : 0u;
-		if (s.depth >= 31)
+		if ((s.pend_term & s.pend_child) != -1 || s.depth == 0) {
+			/* a container that matters: a captured value, a
+			 * context to enter, or the top-level value */
+			if (s.pend_term >= 0) {
+				slots[s.pend_term] = (u64)pos;	/* end 0 */
+				s.set_mask |= 1u << s.pend_term;
+			}
+			int enter = -1;
+			if (s.pend_child >= 0) {
+				s.set_mask &= ~P.ctx[s.pend_child].subtree_mask;
+				enter = s.pend_child;
+			} else if (s.depth == 0 && P.nctx) {
+				enter = 0;
+			}
+			if (enter >= 0 && isobj) {
+				s.ctx = enter;
+				s.ctx_depth = (int)s.depth + 1;
+			}
+			s.pend_term = -1;
+			s.pend_child = -1;
+			s.arm &= ~VAL;
+		}
+		s.depth++;
+		if (s.depth == 32) {
+			s.depth = 31;
 			s.state = FS_FB;
-		if (s.pend_term >= 0) {
-			slots[s.pend_term] = (u64)pos;	/* end 0: container */
-			s.set_mask |= 1u << s.pend_term;
 		}
-		int enter = -1;
-		if (s.pend_child >= 0) {
-			s.set_mask &= ~P.ctx[s.pend_child].subtree_mask;
-			enter = s.pend_child;
-		} else if (s.depth == 0 && P.nctx) {
-			enter = 0;
-		}
-		if (enter >= 0 && isobj) {
-			s.ctx = enter;
-			s.ctx_depth = (int)s.depth + 1;
-		}
-		s.pend_term = -1;
-		s.pend_child = -1;
-		s.arm &= ~VAL;
-		s.depth = (s.depth + 1) & 31;
 		s.types = (s.types & ~(1u << s.depth)) | (isobj << s.depth);
 	}
 	if (f & FE_POP) {
-		if ((int)s.depth == s.ctx_depth && s.ctx >= 0) {
+		if ((int)s.depth == s.ctx_depth) {	/* ctx_depth 0 = none */
 			s.ctx = P.ctx[s.ctx].parent;
 			s.ctx_depth--;
 		}
 		s.depth = (s.depth - 1) & 31;
 		s.state = s.depth == 0 ? (u32)FS_DONE :
-		    ((s.types >> s.depth) & 1) ? (u32)FS_AFTER_O : (u32)FS_AFTER_A;
+		    (u32)FS_AFTER_A - ((s.types >> s.depth) & 1);
 	}
 }
 
@@ -1179,6 +1185,22 @@ dropped:
 	if (ovf)
 		C.unsupported++;
 	return 0;
+}
+
+/* same hash, key given as aligned 64-bit words (little endian) */
+DNG_HD u64 key_hash_words(const unsigned long long *kw, u32 klen)
+{
+	u64 h = 0x9E3779B97F4A7C15ull ^ ((u64)klen * 0xff51afd7ed558ccdull);
+	u32 n = (klen + 7) >> 3;
+	for (u32 i = 0; i < n; i++) {
+		h ^= kw[i];
+		h *= 0xff51afd7ed558ccdull;
+		h ^= h >> 32;
+	}
+	h ^= h >> 29;
+	h *= 0xc4ceb9fe1a85ec53ull;
+	h ^= h >> 32;
+	return h;
 }
 
 /* 64-bit hash of an encoded key (klen rounded up to 8, zero padded) */

@@ -75,10 +75,10 @@ struct GTable {
 
 struct SSlot {
 	unsigned long long tag;
-	unsigned long long count;
+	u32 count_lo, count_hi;		/* 64-bit tally as two native 32-bit atomics */
 	u32 klen;
 	u32 pad;
-	u8 key[DNG_SKEY];
+	unsigned long long key[DNG_SKEY / 8];	/* zero padded */
 };
 
 struct ScanArgs {
@@ -158,9 +158,21 @@ __device__ __forceinline__ void global_add(const GTable &t, u64 h,
 
 /* ---- shared table --------------------------------------------------------- */
 
-__device__ __forceinline__ void shared_add(SSlot *tab, const GTable &gt, u64 h,
-    const u8 *key, u32 klen, unsigned long long w)
+__device__ __forceinline__ void slot_count(SSlot *s, unsigned long long w)
 {
+	u32 lo = (u32)w, hi = (u32)(w >> 32);
+	u32 old = atomicAdd(&s->count_lo, lo);
+	if (old + lo < old)
+		hi++;			/* carry */
+	if (hi)
+		atomicAdd(&s->count_hi, hi);
+}
+
+/* key: klen bytes, zero padded to a multiple of 8, 8-byte aligned */
+__device__ __forceinline__ void shared_add(SSlot *tab, const GTable &gt, u64 h,
+    const unsigned long long *key, u32 klen, unsigned long long w)
+{
+	const u32 nw = (klen + 7) >> 3;
 	if (klen <= DNG_SKEY) {
 		unsigned long long claim = (h | 1ull) & ~DNG_READY;
 		u32 idx = (u32)(h >> 40) & (DNG_SSLOTS - 1);
@@ -173,9 +185,9 @@ __device__ __forceinline__ void shared_add(SSlot *tab, const GTable &gt, u64 h,
 				    atomicCAS(&s->tag, 0ull, claim);
 				if (old == 0) {
 					s->klen = klen;
-					for (u32 k = 0; k < klen; k++)
+					for (u32 k = 0; k < nw; k++)
 						s->key[k] = key[k];
-					atomicAdd(&s->count, w);
+					slot_count(s, w);
 					__threadfence_block();
 					*(volatile unsigned long long *)&s->tag =
 					    claim | DNG_READY;
@@ -189,12 +201,13 @@ __device__ __forceinline__ void shared_add(SSlot *tab, const GTable &gt, u64 h,
 					    &s->tag;
 				__threadfence_block();
 				if (*(volatile u32 *)&s->klen == klen) {
-					const volatile u8 *sk = s->key;
+					const volatile unsigned long long *sk =
+					    s->key;
 					u32 k = 0;
-					while (k < klen && sk[k] == key[k])
+					while (k < nw && sk[k] == key[k])
 						k++;
-					if (k == klen) {
-						atomicAdd(&s->count, w);
+					if (k == nw) {
+						slot_count(s, w);
 						return;
 					}
 				}
@@ -202,7 +215,7 @@ __device__ __forceinline__ void shared_add(SSlot *tab, const GTable &gt, u64 h,
 			idx = (idx + 1) & (DNG_SSLOTS - 1);
 		}
 	}
-	global_add(gt, h, key, klen, w);
+	global_add(gt, h, (const u8 *)key, klen, w);
 }
 
 /* ---- TMA / mbarrier helpers ----------------------------------------------- */
@@ -274,12 +287,13 @@ __device__ __forceinline__ void scan_tail(const u8 *rec, u32 len,
     const DevPlan &P, RecState &R, SSlot *stab, const GTable &gt,
     LocalCounters &C)
 {
-	u8 kbuf[KEY_MAX + 16];
+	__align__(8) u8 kbuf[KEY_MAX + 16];
 	u32 klen;
 	u64 w;
 	if (process_record(rec, len, P, R, C, kbuf, klen, w)) {
-		u64 h = key_hash(kbuf, klen);
-		shared_add(stab, gt, h, kbuf, klen, w);
+		const unsigned long long *kw = (const unsigned long long *)kbuf;
+		u64 h = key_hash_words(kw, klen);
+		shared_add(stab, gt, h, kw, klen, w);
 	}
 }
 
@@ -446,10 +460,15 @@ scan_kernel(const ScanArgs a)
 					uint4 v = *(const uint4 *)(sdata + p);
 					u32 mm[4] = { nl_mask(v.x), nl_mask(v.y),
 					    nl_mask(v.z), nl_mask(v.w) };
+					if (!(mm[0] | mm[1] | mm[2] | mm[3]))
+						continue;
+					const bool partial = p + 16 > c1 || p < lower;
 #pragma unroll
 					for (u32 q = 0; q < 4; q++) {
-						u32 m = mm[q] & byte_range_mask(
-						    p + 4 * q, lower, c1);
+						u32 m = mm[q];
+						if (partial)
+							m &= byte_range_mask(p + 4 * q,
+							    lower, c1);
 						while (m) {
 							u32 b = (__ffs(m) - 1) >> 3;
 							m &= m - 1;
@@ -552,8 +571,10 @@ scan_kernel(const ScanArgs a)
 		if (s->tag != 0) {
 			/* slots are zero-initialised and written once, so
 			 * s->key is already zero padded for key_hash() */
-			global_add(a.tab, key_hash(s->key, s->klen), s->key,
-			    s->klen, s->count);
+			global_add(a.tab, key_hash_words(s->key, s->klen),
+			    (const u8 *)s->key, s->klen,
+			    ((unsigned long long)s->count_hi << 32) |
+			    s->count_lo);
 		}
 	}
 
