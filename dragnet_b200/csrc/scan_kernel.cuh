@@ -261,6 +261,35 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
 	    :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ u32 lds32(u32 addr)
+{
+	u32 v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
+__device__ __forceinline__ u32 lds8(u32 addr)
+{
+	u32 v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
+__device__ __forceinline__ u32 lds16(u32 addr)
+{
+	u32 v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
+/* one automaton step on a class code (see record.cuh fast_step) */
+#define FAST_STEP(cc, pos) do {						\
+	u32 e_ = lds16(trb + (fs.state * FAST_NCLS + (cc)) * 2);	\
+	fs.state = e_ & 0xff;						\
+	if ((e_ >> 8) & fs.arm)						\
+		fast_event(fs, P, R.slots, e_ >> 8, (pos));		\
+} while (0)
+
 /* exact per-byte equality mask: 0x80 in every byte of w equal to 0x0a */
 __device__ __forceinline__ u32 nl_mask(u32 w)
 {
@@ -528,9 +557,35 @@ scan_kernel(const ScanArgs a)
 				const u8 *rec = sdata + (fast ? beg : 0);
 				u32 trip = __reduce_max_sync(0xffffffffu,
 				    fast ? len + 1 : 0);
-#pragma unroll 4
-				for (u32 i = 0; i < trip; i++)
-					fast_step(fs, P, R.slots, rec[i], i);
+				/*
+				 * Four bytes per round: one aligned 32-bit shared
+				 * load (+ funnel shift for the record's byte
+				 * alignment) and four independent class lookups are
+				 * issued up front; only the state transition itself
+				 * is a dependent chain.
+				 */
+				{
+					const u32 ra = smem_u32(rec);
+					const u32 sh = (ra & 3) * 8;
+					u32 wa = ra & ~3u;
+					u32 w0 = lds32(wa);
+					const u32 clsb = smem_u32(P.fast.cls);
+					const u32 trb = smem_u32(P.fast.trans);
+					for (u32 i = 0; i < trip; i += 4) {
+						wa += 4;
+						u32 w1 = lds32(wa);
+						u32 w = __funnelshift_r(w0, w1, sh);
+						w0 = w1;
+						u32 c0 = lds8(clsb + (w & 0xff));
+						u32 c1 = lds8(clsb + ((w >> 8) & 0xff));
+						u32 c2 = lds8(clsb + ((w >> 16) & 0xff));
+						u32 c3 = lds8(clsb + (w >> 24));
+						FAST_STEP(c0, i);
+						FAST_STEP(c1, i + 1);
+						FAST_STEP(c2, i + 2);
+						FAST_STEP(c3, i + 3);
+					}
+				}
 				if (fast && fs.state == FS_FIN) {
 					C.lines++;
 					fast_finish(rec, fs, R);
