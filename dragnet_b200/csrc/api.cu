@@ -55,6 +55,7 @@ struct dng_scan {
 	dng_plan plan;
 	int device = 0;
 	int sm_count = 0;
+	u32 plan_bytes = 0;
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
 	cudaStream_t own_stream = nullptr;
 	DevPlan *d_plan = nullptr;
@@ -128,10 +129,11 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 	a.tab = s->tab;
 	a.ntiles = (u32)((nbytes + DNG_TILE - 1) / DNG_TILE);
 	a.final = final ? 1 : 0;
+	a.plan_bytes = s->plan_bytes;
 	u32 grid = std::min<u32>(a.ntiles, (u32)s->sm_count * DNG_CTAS_PER_SM);
 	cudaEvent_t e0 = get_event(s), e1 = get_event(s);
 	cudaEventRecord(e0, s->stream);
-	scan_kernel<<<grid, DNG_NT, SMEM_TOTAL, s->stream>>>(a);
+	scan_kernel<<<grid, DNG_NT, SMEM_FIXED + s->plan_bytes, s->stream>>>(a);
 	cudaEventRecord(e1, s->stream);
 	s->ev_pairs.emplace_back(e0, e1);
 	s->launches++;
@@ -284,9 +286,11 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		    "cudaGetDeviceProperties")))
 			break;
 		s->sm_count = prop.multiProcessorCount;
+		s->plan_bytes = devplan_smem_bytes(plan->dev);
 		if ((rc = s->cuda(cudaFuncSetAttribute(scan_kernel,
 		    cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    (int)SMEM_TOTAL), "cudaFuncSetAttribute")))
+		    (int)(SMEM_FIXED + sizeof (DevPlan))),
+		    "cudaFuncSetAttribute")))
 			break;
 		if ((rc = s->cuda(cudaStreamCreateWithFlags(&s->stream,
 		    cudaStreamNonBlocking), "cudaStreamCreate")))

@@ -229,6 +229,7 @@ struct JParser {
 
 struct FastBuilder {
 	FastTab &F;
+	u16 *TR;		/* FAST_MAXSTATES x FAST_NCLS while building */
 	int nstates = 10;	/* FS_* are fixed */
 	int ncls = 0;
 
@@ -237,11 +238,11 @@ struct FastBuilder {
 	    C_DOT, C_ZERO, C_DIGIT, C_a, C_b, C_cd, C_e, C_f, C_l, C_n, C_r, C_s,
 	    C_t, C_u, C_AF, C_E, C_SLASH, C_WSC, C_BASE_COUNT };
 
-	explicit FastBuilder(FastTab &f) : F(f) {}
+	FastBuilder(FastTab &f, u16 *tr) : F(f), TR(tr) {}
 
 	int alloc() { return nstates < FAST_MAXSTATES ? nstates++ : -1; }
 	void set(int st, int cls, int next, int flags = 0) {
-		F.trans[st * FAST_NCLS + cls] = (u16)(next | (flags << 8));
+		TR[st * FAST_NCLS + cls] = (u16)(next | (flags << 8));
 	}
 	void set_all(int st, int next) {
 		for (int c = 0; c < FAST_NCLS; c++)
@@ -275,7 +276,8 @@ struct FastBuilder {
 	    const std::vector<std::vector<int>> &key_term,	/* [ctx][key] */
 	    const std::vector<std::vector<int>> &key_child) {
 		memset(&F, 0, sizeof (F));
-		if (keys.size() > FAST_MAXKEYS)
+		memset(TR, 0, sizeof (u16) * FAST_MAXSTATES * FAST_NCLS);
+		if (keys.size() > FAST_MAXKEYS || key_term.size() > FAST_MAXCTX)
 			return false;
 		/* classes: base classes, then one per distinct key byte */
 		int base_of[FAST_NCLS];
@@ -466,8 +468,7 @@ struct FastBuilder {
 		/* tab and CR are whitespace between tokens but control
 		 * characters inside strings and keys */
 		for (int st = 0; st < nstates; st++)
-			F.trans[st * FAST_NCLS + C_WSC] =
-			    F.trans[st * FAST_NCLS + C_WS];
+			TR[st * FAST_NCLS + C_WSC] = TR[st * FAST_NCLS + C_WS];
 		for (int x = 0; x < 2; x++)
 			set(S[x], C_WSC, FS_ERR);
 		set(KX, C_WSC, FS_ERR);
@@ -484,8 +485,8 @@ struct FastBuilder {
 							if (F.cls[kv.first] == c)
 								trie_edge = true;
 				if (!trie_edge)
-					F.trans[st * FAST_NCLS + c] =
-					    F.trans[st * FAST_NCLS + base_of[c]];
+					TR[st * FAST_NCLS + c] =
+					    TR[st * FAST_NCLS + base_of[c]];
 			}
 		}
 		/* candidate map */
@@ -498,6 +499,13 @@ struct FastBuilder {
 				    (u8)key_child[c][g];
 			}
 		}
+		/* compact the rows to the classes actually used */
+		int stride = (ncls + 3) & ~3;
+		for (int st = 0; st < nstates; st++)
+			for (int c = 0; c < stride; c++)
+				TR[st * stride + c] = c < ncls ?
+				    TR[st * FAST_NCLS + c] : (u16)FS_ERR;
+		F.stride = (u8)stride;
 		F.ok = 1;
 		return true;
 	}
@@ -973,7 +981,7 @@ struct Compiler {
 					kc[c][g] = cr.child_ctx;
 				}
 			}
-			FastBuilder fb(P.fast);
+			FastBuilder fb(P.fast, P.trans);
 			if (arraylike || !fb.build(keys, kt, kc))
 				P.fast.ok = 0;
 		}

@@ -39,8 +39,8 @@ enum : u8 {
 
 enum : int {
 	MAX_SLOTS = 32, MAX_CTX = 24, MAX_CANDS = 64, MAX_PATHS = 24,
-	MAX_LEVELS = 8, MAX_CODE = 64, MAX_SYN = 8, MAX_COLS = 12,
-	POOL_BYTES = 3072, KEY_MAX = 512
+	MAX_LEVELS = 8, MAX_CODE = 48, MAX_SYN = 8, MAX_COLS = 12,
+	POOL_BYTES = 2048, KEY_MAX = 512
 };
 
 /* record flags produced by the parser */
@@ -111,7 +111,8 @@ enum : u8 { FMT_JSON = 0, FMT_SKINNER = 1 };
  * keys, nesting > 31, a top-level scalar) ends in FS_FB and the record is
  * re-parsed by the general parser (parse_record).
  */
-enum : int { FAST_NCLS = 64, FAST_MAXSTATES = 128, FAST_MAXKEYS = 48 };
+enum : int { FAST_NCLS = 64, FAST_MAXSTATES = 128, FAST_MAXKEYS = 48,
+	FAST_MAXCTX = 12 };
 enum : u8 {			/* event flags (high byte of a transition) */
 	FE_PUSH = 1, FE_POP = 2, FE_OBJ = 4, FE_KEYHIT = 8,
 	FE_VALSTART = 16, FE_VALEND_INCL = 32, FE_VALEND_EXCL = 64
@@ -122,13 +123,13 @@ enum : u8 {			/* fixed state numbers */
 };
 
 struct FastTab {
-	u16 trans[FAST_MAXSTATES * FAST_NCLS];
 	u8 cls[256];
-	u8 candmap[MAX_CTX * FAST_MAXKEYS][2];	/* [ctx][key] -> term, child */
+	u8 candmap[FAST_MAXCTX * FAST_MAXKEYS][2];	/* [ctx][key] -> term, child */
 	u8 ok;			/* tables are valid for this plan */
 	u8 nstates, nkeys;
 	u8 kc_base;		/* state kc_base + g = "key g just closed" */
-	u8 pad[4];
+	u8 stride;		/* classes per row of trans[] (<= FAST_NCLS) */
+	u8 pad[3];
 };
 
 struct DevPlan {
@@ -146,7 +147,19 @@ struct DevPlan {
 	u8 pad[3];
 	char pool[POOL_BYTES];
 	FastTab fast;
+	/* LAST: only the first fast.nstates rows of fast.stride entries are
+	 * meaningful; CTAs copy just that prefix into shared memory */
+	u16 trans[FAST_MAXSTATES * FAST_NCLS];
 };
+
+/* bytes of a DevPlan a CTA needs in shared memory */
+static inline u32 devplan_smem_bytes(const DevPlan &p)
+{
+	u32 rows = p.fast.ok ? p.fast.nstates : 0;
+	u32 n = (u32)((const char *)p.trans - (const char *)&p) +
+	    rows * p.fast.stride * 2u;
+	return (n + 127u) & ~127u;
+}
 
 } /* namespace dng */
 

@@ -613,7 +613,7 @@ DNG_HD void fast_event(FastState &s, const DevPlan &P, u64 *slots, u32 f,
 
 DNG_HD void fast_step(FastState &s, const DevPlan &P, u64 *slots, u32 c, u32 pos)
 {
-	u32 e = P.fast.trans[s.state * FAST_NCLS + P.fast.cls[c]];
+	u32 e = P.trans[s.state * P.fast.stride + P.fast.cls[c]];
 	s.state = e & 0xff;
 	u32 f = e >> 8;
 	if (f & s.arm)

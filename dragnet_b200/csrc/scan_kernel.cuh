@@ -30,7 +30,7 @@
 namespace dng {
 
 #ifndef DNG_NT
-#define DNG_NT 256			/* threads per CTA */
+#define DNG_NT 384			/* threads per CTA */
 #endif
 #ifndef DNG_TILE
 /* bytes of input a tile owns: DNG_NT slices of 13 x 16 bytes -- an odd number
@@ -90,17 +90,18 @@ struct ScanArgs {
 	GTable tab;
 	u32 ntiles;
 	u32 final;			/* treat an unterminated tail as a line */
+	u32 plan_bytes;			/* devplan_smem_bytes(plan) */
 };
 
 #define DNG_READY 0x8000000000000000ull
 
-static constexpr size_t SMEM_PLAN = (sizeof (DevPlan) + 127) & ~(size_t)127;
+/* the plan copy is as large as the plan needs (devplan_smem_bytes) */
 static constexpr size_t SMEM_TAB = sizeof (SSlot) * DNG_SSLOTS;
 static constexpr size_t SMEM_NL = sizeof (u32) * DNG_NLCAP;
 /* the slack lets lanes of a warp keep stepping (in an absorbing state) past
  * the end of their own short record while a neighbour finishes a longer one */
 static constexpr size_t SMEM_DATA = DNG_PRELAP + DNG_TILE + DNG_FASTMAX + 128;
-static constexpr size_t SMEM_TOTAL = SMEM_PLAN + SMEM_TAB + SMEM_NL + SMEM_DATA;
+static constexpr size_t SMEM_FIXED = SMEM_TAB + SMEM_NL + SMEM_DATA;
 
 /* ---- global table ------------------------------------------------------- */
 
@@ -284,7 +285,7 @@ __device__ __forceinline__ u32 lds16(u32 addr)
 
 /* one automaton step on a class code (see record.cuh fast_step) */
 #define FAST_STEP(cc, pos) do {						\
-	u32 e_ = lds16(trb + (fs.state * FAST_NCLS + (cc)) * 2);	\
+	u32 e_ = lds16(trb + (fs.state * stride + (cc)) * 2);		\
 	fs.state = e_ & 0xff;						\
 	if ((e_ >> 8) & fs.arm)						\
 		fast_event(fs, P, R.slots, e_ >> 8, (pos));		\
@@ -367,9 +368,9 @@ scan_kernel(const ScanArgs a)
 {
 	extern __shared__ __align__(128) u8 smem[];
 	DevPlan *sp = (DevPlan *)smem;
-	SSlot *stab = (SSlot *)(smem + SMEM_PLAN);
-	u32 *nlpos = (u32 *)(smem + SMEM_PLAN + SMEM_TAB);
-	u8 *sdata = smem + SMEM_PLAN + SMEM_TAB + SMEM_NL;
+	SSlot *stab = (SSlot *)(smem + a.plan_bytes);
+	u32 *nlpos = (u32 *)(smem + a.plan_bytes + SMEM_TAB);
+	u8 *sdata = smem + a.plan_bytes + SMEM_TAB + SMEM_NL;
 	__shared__ __align__(8) u64 mbar;
 	__shared__ u32 wsum[DNG_NT / 32];
 	__shared__ u32 s_total;
@@ -381,7 +382,7 @@ scan_kernel(const ScanArgs a)
 	{	/* plan -> shared, clear the table */
 		const uint4 *src = (const uint4 *)a.plan;
 		uint4 *dst = (uint4 *)sp;
-		for (u32 i = tid; i < sizeof (DevPlan) / 16; i += DNG_NT)
+		for (u32 i = tid; i < a.plan_bytes / 16; i += DNG_NT)
 			dst[i] = src[i];
 		uint4 z = make_uint4(0, 0, 0, 0);
 		uint4 *tz = (uint4 *)stab;
@@ -417,6 +418,13 @@ scan_kernel(const ScanArgs a)
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 			mbar_expect_tx(&mbar, bulk);
 			tma_load_1d(sdata, a.data + ws, bulk, &mbar);
+			/* start pulling this CTA's next tile into L2 */
+			unsigned long long nx = g0 +
+			    (unsigned long long)gridDim.x * DNG_TILE;
+			if (nx + DNG_TILE <= a.nbytes)
+				asm volatile("cp.async.bulk.prefetch.L2.global "
+				    "[%0], %1;" :: "l"(a.data + nx),
+				    "r"((u32)DNG_TILE) : "memory");
 		}
 		for (u32 i = bulk + tid; i < wlen; i += DNG_NT)
 			sdata[i] = a.data[ws + i];
@@ -434,6 +442,7 @@ scan_kernel(const ScanArgs a)
 		if (c1 > wlen)
 			c1 = wlen;
 		u32 cnt = 0;
+		u32 hot = 0;		/* bit j: 16-byte word j holds a newline */
 		for (u32 p = c0; p < c1; p += 16) {
 			uint4 v = *(const uint4 *)(sdata + p);
 			u32 m0 = nl_mask(v.x), m1 = nl_mask(v.y);
@@ -445,7 +454,10 @@ scan_kernel(const ScanArgs a)
 				m2 &= byte_range_mask(p + 8, lower, c1);
 				m3 &= byte_range_mask(p + 12, lower, c1);
 			}
-			cnt += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+			u32 k = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+			cnt += k;
+			if (k)
+				hot |= 1u << ((p - c0) >> 4);
 		}
 		/* an unterminated final line ends at a virtual newline */
 		const bool vnl = a.final && we == a.nbytes && tid == DNG_NT - 1 &&
@@ -485,12 +497,11 @@ scan_kernel(const ScanArgs a)
 			/* write this pass's newline positions, in order */
 			u32 idx = mybase;
 			if (idx < pass + DNG_NLCAP && idx + cnt > pass) {
-				for (u32 p = c0; p < c1; p += 16) {
+				for (u32 hm = hot; hm; hm &= hm - 1) {
+					const u32 p = c0 + ((__ffs(hm) - 1) << 4);
 					uint4 v = *(const uint4 *)(sdata + p);
 					u32 mm[4] = { nl_mask(v.x), nl_mask(v.y),
 					    nl_mask(v.z), nl_mask(v.w) };
-					if (!(mm[0] | mm[1] | mm[2] | mm[3]))
-						continue;
 					const bool partial = p + 16 > c1 || p < lower;
 #pragma unroll
 					for (u32 q = 0; q < 4; q++) {
@@ -570,7 +581,8 @@ scan_kernel(const ScanArgs a)
 					u32 wa = ra & ~3u;
 					u32 w0 = lds32(wa);
 					const u32 clsb = smem_u32(P.fast.cls);
-					const u32 trb = smem_u32(P.fast.trans);
+					const u32 trb = smem_u32(P.trans);
+					const u32 stride = P.fast.stride;
 					for (u32 i = 0; i < trip; i += 4) {
 						wa += 4;
 						u32 w1 = lds32(wa);
