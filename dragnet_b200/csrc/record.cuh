@@ -519,22 +519,40 @@ invalid:
 /* ---- fast path: lock-step byte automaton (plan.h FastTab) ----------------- */
 
 struct FastState {
-	u32 state, depth, types, arm, vstart, set_mask;
-	int ctx, ctx_depth, pend_term, pend_child;
+	u32 state;
+	u32 stk;	/* container types, innermost in bit 0 (1 = object), under a
+			 * sentinel 1: stk == 1 means depth 0 */
+	u32 ctx_stk;	/* value of stk while directly inside the context's
+			 * container; 0 = no context */
+	u32 arm, vstart, set_mask;
+	int ctx, pend_term, pend_child;
 };
 
 DNG_HD void fast_init(FastState &s)
 {
 	s.state = FS_START;
-	s.depth = 0;
-	s.types = 0;
+	s.stk = 1;
+	s.ctx_stk = 0;
 	s.arm = FE_PUSH | FE_POP | FE_KEYHIT;
 	s.vstart = 0;
 	s.set_mask = 0;
 	s.ctx = -1;
-	s.ctx_depth = 0;
 	s.pend_term = -1;
 	s.pend_child = -1;
+}
+
+/* the value after a candidate key has ended at `end` (exclusive) */
+DNG_HD void fast_capture(FastState &s, const DevPlan &P, u64 *slots, u32 end)
+{
+	if (s.pend_term >= 0) {
+		slots[s.pend_term] = (u64)s.vstart | ((u64)end << 32);
+		s.set_mask |= 1u << s.pend_term;
+	}
+	if (s.pend_child >= 0)
+		s.set_mask &= ~P.ctx[s.pend_child].subtree_mask;
+	s.pend_term = -1;
+	s.pend_child = -1;
+	s.arm &= ~(u32)(FE_VALSTART | FE_VALEND_INCL | FE_VALEND_EXCL);
 }
 
 /* the divergent part: runs only on bytes whose transition carries an armed
@@ -543,24 +561,53 @@ DNG_HD void fast_event(FastState &s, const DevPlan &P, u64 *slots, u32 f,
     u32 pos)
 {
 	const u32 VAL = FE_VALSTART | FE_VALEND_INCL | FE_VALEND_EXCL;
-	if (f & s.arm & FE_VALSTART)
-		s.vstart = pos;
-	if (f & s.arm & (FE_VALEND_INCL | FE_VALEND_EXCL)) {
-		u32 end = pos + ((f & FE_VALEND_INCL) ? 1u : 0u);
-		if (s.pend_term >= 0) {
-			slots[s.pend_term] = (u64)s.vstart | ((u64)end << 32);
-			s.set_mask |= 1u << s.pend_term;
+	if (f & (FE_PUSH | FE_POP)) {
+		if (f & s.arm & FE_VALEND_EXCL)	/* 123} : value ends here */
+			fast_capture(s, P, slots, pos);
+		if (f & FE_PUSH) {
+			u32 isobj = (f & FE_OBJ) ? 1u : 0u;
+			if ((s.pend_term & s.pend_child) != -1 || s.stk == 1) {
+				/* a container that matters: a captured value,
+				 * a context to enter, or the top-level value */
+				if (s.pend_term >= 0) {
+					slots[s.pend_term] = (u64)pos; /* end 0 */
+					s.set_mask |= 1u << s.pend_term;
+				}
+				int enter = -1;
+				if (s.pend_child >= 0) {
+					s.set_mask &=
+					    ~P.ctx[s.pend_child].subtree_mask;
+					enter = s.pend_child;
+				} else if (s.stk == 1 && P.nctx) {
+					enter = 0;
+				}
+				if (enter >= 0 && isobj) {
+					s.ctx = enter;
+					s.ctx_stk = (s.stk << 1) | 1u;
+				}
+				s.pend_term = -1;
+				s.pend_child = -1;
+				s.arm &= ~VAL;
+			}
+			if (s.stk >> 30)
+				s.state = FS_FB;	/* too deep for 32 bits */
+			else
+				s.stk = (s.stk << 1) | isobj;
+		} else {
+			if (s.stk == s.ctx_stk) {	/* leaving the context */
+				s.ctx = P.ctx[s.ctx].parent;
+				s.ctx_stk = s.ctx >= 0 ? s.stk >> 1 : 0;
+			}
+			s.stk >>= 1;
+			s.state = s.stk == 1 ? (u32)FS_DONE :
+			    (u32)FS_AFTER_A - (s.stk & 1);
 		}
-		if (s.pend_child >= 0)
-			s.set_mask &= ~P.ctx[s.pend_child].subtree_mask;
-		s.pend_term = -1;
-		s.pend_child = -1;
-		s.arm &= ~VAL;
+		return;
 	}
 	if (f & FE_KEYHIT) {
 		u32 g = s.state - P.fast.kc_base;
 		s.state = FS_KC;
-		if ((int)s.depth == s.ctx_depth && s.ctx >= 0) {
+		if (s.stk == s.ctx_stk) {
 			const u8 *cm = P.fast.candmap[s.ctx * FAST_MAXKEYS + g];
 			if (cm[0] != 0xFF || cm[1] != 0xFF) {
 				s.pend_term = (int8_t)cm[0];
@@ -568,47 +615,12 @@ DNG_HD void fast_event(FastState &s, const DevPlan &P, u64 *slots, u32 f,
 				s.arm |= VAL;
 			}
 		}
+		return;
 	}
-	if (f & FE_PUSH) {
-		u32 isobj = (f & FE_OBJ) ? 1u : 0u;
-		if ((s.pend_term & s.pend_child) != -1 || s.depth == 0) {
-			/* a container that matters: a captured value, a
-			 * context to enter, or the top-level value */
-			if (s.pend_term >= 0) {
-				slots[s.pend_term] = (u64)pos;	/* end 0 */
-				s.set_mask |= 1u << s.pend_term;
-			}
-			int enter = -1;
-			if (s.pend_child >= 0) {
-				s.set_mask &= ~P.ctx[s.pend_child].subtree_mask;
-				enter = s.pend_child;
-			} else if (s.depth == 0 && P.nctx) {
-				enter = 0;
-			}
-			if (enter >= 0 && isobj) {
-				s.ctx = enter;
-				s.ctx_depth = (int)s.depth + 1;
-			}
-			s.pend_term = -1;
-			s.pend_child = -1;
-			s.arm &= ~VAL;
-		}
-		s.depth++;
-		if (s.depth == 32) {
-			s.depth = 31;
-			s.state = FS_FB;
-		}
-		s.types = (s.types & ~(1u << s.depth)) | (isobj << s.depth);
-	}
-	if (f & FE_POP) {
-		if ((int)s.depth == s.ctx_depth) {	/* ctx_depth 0 = none */
-			s.ctx = P.ctx[s.ctx].parent;
-			s.ctx_depth--;
-		}
-		s.depth = (s.depth - 1) & 31;
-		s.state = s.depth == 0 ? (u32)FS_DONE :
-		    (u32)FS_AFTER_A - ((s.types >> s.depth) & 1);
-	}
+	if (f & s.arm & FE_VALSTART)
+		s.vstart = pos;
+	if (f & s.arm & (FE_VALEND_INCL | FE_VALEND_EXCL))
+		fast_capture(s, P, slots, pos + ((f & FE_VALEND_INCL) ? 1u : 0u));
 }
 
 DNG_HD void fast_step(FastState &s, const DevPlan &P, u64 *slots, u32 c, u32 pos)
