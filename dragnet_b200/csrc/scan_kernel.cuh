@@ -44,7 +44,8 @@ namespace dng {
 #define DNG_CTAS_PER_SM 2
 #define DNG_NLCAP 1024			/* newline positions per pass */
 #define DNG_SSLOTS 128			/* shared hash table slots */
-#define DNG_FASTMAX 1024		/* longest line the lock-step automaton takes */
+#define DNG_FASTMAX 16384		/* longest line the lock-step automaton takes */
+#define DNG_SLACK 1024			/* readable bytes past the staged window */
 #define DNG_SKEY 40			/* inline key bytes per shared slot */
 #define DNG_MAXREC (1u << 24)		/* longest line handled */
 
@@ -100,7 +101,7 @@ static constexpr size_t SMEM_TAB = sizeof (SSlot) * DNG_SSLOTS;
 static constexpr size_t SMEM_NL = sizeof (u32) * DNG_NLCAP;
 /* the slack lets lanes of a warp keep stepping (in an absorbing state) past
  * the end of their own short record while a neighbour finishes a longer one */
-static constexpr size_t SMEM_DATA = DNG_PRELAP + DNG_TILE + DNG_FASTMAX + 128;
+static constexpr size_t SMEM_DATA = DNG_PRELAP + DNG_TILE + DNG_SLACK + 128;
 static constexpr size_t SMEM_FIXED = SMEM_TAB + SMEM_NL + SMEM_DATA;
 
 /* ---- global table ------------------------------------------------------- */
@@ -579,12 +580,17 @@ scan_kernel(const ScanArgs a)
 					const u32 ra = smem_u32(rec);
 					const u32 sh = (ra & 3) * 8;
 					u32 wa = ra & ~3u;
+					/* lanes idling past their own line while a
+					 * neighbour finishes a longer one must not
+					 * run off the staged window */
+					const u32 wlim = smem_u32(sdata) +
+					    DNG_PRELAP + DNG_TILE + DNG_SLACK;
 					u32 w0 = lds32(wa);
 					const u32 clsb = smem_u32(P.fast.cls);
 					const u32 trb = smem_u32(P.trans);
 					const u32 stride = P.fast.stride;
 					for (u32 i = 0; i < trip; i += 4) {
-						wa += 4;
+						wa = min(wa + 4, wlim);
 						u32 w1 = lds32(wa);
 						u32 w = __funnelshift_r(w0, w1, sh);
 						w0 = w1;

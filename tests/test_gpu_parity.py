@@ -145,6 +145,27 @@ def test_device_generator_is_byte_identical_and_feed_device_matches():
     assert c.flat_counters['lines'] == n
 
 
+def test_medium_lines_take_the_lock_step_path(tmp_path):
+    """1-16 KB lines mixed with short ones: warps whose lanes hold lines of
+    very different lengths (the automaton idles in an absorbing state)."""
+    import random
+    rng = random.Random(7)
+    lines = []
+    for i in range(4000):
+        pad = rng.choice([0, 0, 0, 50, 900, 1500, 3000, 6000, 12000])
+        lines.append(b'{"a":"k%d","pad":"' % (i % 7) + b'x' * pad +
+                     b'","n":{"b":[1,{"c":"\\"}]},"z":%d}' % i)
+    lines[100] = lines[100][:-1]                    # invalid
+    lines[200] = b'{"a":"esc\u0041","pad":"' + b'y' * 5000 + b'"}'
+    path = _write(tmp_path, 'medium.log', lines)
+    for argv in (['-b', 'a'], ['-b', 'n.b.length'], []):
+        plan = corpus.make_plan(argv)
+        exp_p, exp_c = py_engine(plan, [path])
+        act_p, act_c = gpu_engine(plan, [path])
+        assert canon_points(act_p) == canon_points(exp_p), argv
+        assert act_c == exp_c, argv
+
+
 def test_long_lines_and_large_counts(tmp_path):
     """Lines longer than the staged window take the HBM path; many small
     lines exercise the multi-pass newline index."""
