@@ -154,9 +154,9 @@ def test_medium_lines_take_the_lock_step_path(tmp_path):
     for i in range(4000):
         pad = rng.choice([0, 0, 0, 50, 900, 1500, 3000, 6000, 12000])
         lines.append(b'{"a":"k%d","pad":"' % (i % 7) + b'x' * pad +
-                     b'","n":{"b":[1,{"c":"\\"}]},"z":%d}' % i)
+                     b'","n":{"b":[1,{"c":"\\\\"}]},"z":%d}' % i)
     lines[100] = lines[100][:-1]                    # invalid
-    lines[200] = b'{"a":"esc\u0041","pad":"' + b'y' * 5000 + b'"}'
+    lines[200] = b'{"a":"esc\\u0041","pad":"' + b'y' * 5000 + b'"}'
     path = _write(tmp_path, 'medium.log', lines)
     for argv in (['-b', 'a'], ['-b', 'n.b.length'], []):
         plan = corpus.make_plan(argv)
