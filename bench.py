@@ -387,6 +387,25 @@ def gpu_arm(args, rank, local_rank, world):
                                    for c in cols)
                            for cols, _ in E['last'][0])
 
+    # ---- files: the same pool as a tmpfs file through dng_scan_feed_file -------
+    file_leg = None
+    if world == 1 and args.file_steps > 0:
+        d = '/dev/shm' if os.path.isdir('/dev/shm') else tempfile.gettempdir()
+        fpath = os.path.join(d, 'dnbench_pool_%d.ndjson' % os.getpid())
+        host_pool.numpy().tofile(fpath)
+        try:
+            Fr = timed(lambda s: s.feed_file(fpath), args.file_steps, 1)
+            fms = Fr['dev_ms'] / args.file_steps
+            file_leg = {'value': pool_rows / (fms / 1e3),
+                        'unit': 'records/s', 'ms_per_step': fms,
+                        'file_bytes': pool_len,
+                        'gbs': pool_len / 1e9 / (fms / 1e3),
+                        'note': 'dng_scan_feed_file on a page-cache-resident '
+                                'file: reader threads pread into a pinned '
+                                'ring, H2D overlapped with the scan'}
+        finally:
+            os.unlink(fpath)
+
     # ---- N > 1: the merged tallies must equal the sum of the per-rank ones ----
     merge_parity = None
     if world > 1:
@@ -489,6 +508,7 @@ def gpu_arm(args, rank, local_rank, world):
         'clocks': R['clocks'],
         'parity': parity,
         'merge_parity': merge_parity,
+        'e2e_file': file_leg,
     }
     if cpu:
         line['cpu_baseline'] = cpu
@@ -510,6 +530,7 @@ def main():
     ap.add_argument('--pool-rows', type=int, default=10000000)
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--cpu-rows', type=int, default=4000000)
+    ap.add_argument('--file-steps', type=int, default=2)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
