@@ -330,10 +330,11 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		s->tab.arena_cap = (u32)arena;
 		cudaMemset(s->tab.entries, 0, c2 * sizeof (GEntry));
 		cudaMemset(s->tab.misc, 0, 16 * sizeof (u32));
+		const size_t nctr = NCTR + (MAX_METRICS - 1) * MCTR_PER;
 		if ((rc = s->cuda(cudaMalloc(&s->d_counters,
-		    NCTR * sizeof (unsigned long long)), "cudaMalloc counters")))
+		    nctr * sizeof (unsigned long long)), "cudaMalloc counters")))
 			break;
-		cudaMemset(s->d_counters, 0, NCTR * sizeof (unsigned long long));
+		cudaMemset(s->d_counters, 0, nctr * sizeof (unsigned long long));
 		if ((rc = s->cuda(cudaMalloc(&s->d_nl,
 		    2 * sizeof (unsigned long long)), "cudaMalloc nl")))
 			break;
@@ -742,15 +743,49 @@ int dng_scan_counters(dng_scan *s, dng_counters *out)
 		out->ds_ninputs = n;
 		n -= out->ds_filtered + out->ds_failedeval;
 	}
-	if (P.user_entry >= 0) {
+	if (P.metric[0].user_entry >= 0) {
 		out->user_ninputs = n;
 		n -= out->user_filtered + out->user_failedeval;
 	}
-	if (P.nsyn) {
+	if (P.metric[0].nsyn) {
 		out->synth_ninputs = n;
 		n -= out->synth_undef + out->synth_baddate;
 	}
-	if (P.time_entry >= 0)
+	if (P.metric[0].time_entry >= 0)
+		out->time_ninputs = n;
+	return DNG_OK;
+}
+
+int dng_scan_counters_metric(dng_scan *s, int m, dng_counters *out)
+{
+	if (!s || !out || m < 0 || m >= s->plan.dev.nmetrics)
+		return DNG_EINVAL;
+	int rc = dng_scan_counters(s, out);
+	if (rc || m == 0)
+		return rc;
+	unsigned long long c[MCTR_PER];
+	CK(s, cudaMemcpy(c, s->d_counters + NCTR + (m - 1) * MCTR_PER,
+	    sizeof (c), cudaMemcpyDeviceToHost));
+	const Metric &M = s->plan.dev.metric[m];
+	uint64_t n = out->lines - out->invalid_json - out->invalid_point -
+	    out->ds_filtered - out->ds_failedeval;
+	out->user_ninputs = out->synth_ninputs = out->time_ninputs = 0;
+	out->user_filtered = c[0];
+	out->user_failedeval = c[1];
+	out->synth_undef = c[2];
+	out->synth_baddate = c[3];
+	out->time_filtered = c[4];
+	out->time_failedeval = c[5];
+	out->aggr_ninputs = c[6];
+	if (M.user_entry >= 0) {
+		out->user_ninputs = n;
+		n -= c[0] + c[1];
+	}
+	if (M.nsyn) {
+		out->synth_ninputs = n;
+		n -= c[2] + c[3];
+	}
+	if (M.time_entry >= 0)
 		out->time_ninputs = n;
 	return DNG_OK;
 }
@@ -787,7 +822,6 @@ int dng_scan_finish(dng_scan *s, dng_result **out)
 	u32 n = misc[1];
 	dng_result *r = new dng_result();
 	r->init_from_plan(&s->plan);
-	uint64_t total = 0;
 	if (n) {
 		OutEntry *d_out = nullptr;
 		u32 *d_n = nullptr;
@@ -813,10 +847,9 @@ int dng_scan_finish(dng_scan *s, dng_result **out)
 			r->keys.emplace_back((const char *)arena.data() +
 			    ents[i].koff, ents[i].klen);
 			r->values.push_back(ents[i].count);
-			total += ents[i].count;
 		}
 	}
-	r->finalize(total);
+	r->finalize();
 	*out = r;
 	return DNG_OK;
 }
@@ -904,7 +937,25 @@ size_t dng_result_count(const dng_result *r)
 
 size_t dng_result_ncols(const dng_result *r)
 {
-	return r ? (size_t)r->ncols : 0;
+	size_t n = 0;
+	for (int m = 0; r && m < r->nmetrics; m++)
+		n = std::max(n, (size_t)r->ncols[m]);
+	return n;		/* widest metric; == ncols for a plain scan */
+}
+
+size_t dng_result_nmetrics(const dng_result *r)
+{
+	return r ? (size_t)r->nmetrics : 0;
+}
+
+size_t dng_result_ncols_metric(const dng_result *r, int m)
+{
+	return r && m >= 0 && m < r->nmetrics ? (size_t)r->ncols[m] : 0;
+}
+
+int dng_result_metric(const dng_result *r, size_t i)
+{
+	return r && i < r->metric.size() ? r->metric[i] : -1;
 }
 
 int dng_result_get(const dng_result *r, size_t i, const char **strs,
@@ -912,8 +963,8 @@ int dng_result_get(const dng_result *r, size_t i, const char **strs,
 {
 	if (!r || i >= r->keys.size())
 		return DNG_EINVAL;
-	for (int j = 0; j < r->ncols; j++) {
-		const dng_result::Cell &c = r->cells[i * r->ncols + j];
+	for (int j = 0; j < r->ncols[r->metric[i]]; j++) {
+		const dng_result::Cell &c = r->cells[r->cell0[i] + j];
 		if (is_number)
 			is_number[j] = c.is_number;
 		if (numvals)

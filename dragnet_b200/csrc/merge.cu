@@ -80,19 +80,23 @@ int dng_result_from_points(const dng_plan *plan, size_t npoints,
 	dng_result *r = new dng_result();
 	r->init_from_plan(plan);
 	std::vector<std::pair<std::string, uint64_t>> rows;
-	uint64_t total = 0;
+	if (r->nmetrics != 1) {
+		delete r;
+		return DNG_EINVAL;	/* points of one metric only */
+	}
+	const int nc = r->ncols[0];
 	for (size_t i = 0; i < npoints; i++) {
 		std::string k;
-		for (int j = 0; j < r->ncols; j++) {
-			size_t x = i * r->ncols + j;
-			if (r->col_kind[j] == dng::COL_DISCRETE) {
+		for (int j = 0; j < nc; j++) {
+			size_t x = i * nc + j;
+			if (r->col_kind[0][j] == dng::COL_DISCRETE) {
 				size_t n = strlens[x];
 				k += (char)(n & 0xff);
 				k += (char)((n >> 8) & 0xff);
 				k.append(strs[x], n);
 			} else {
 				double v = numvals[x], o;
-				if (r->col_kind[j] == dng::COL_P2) {
+				if (r->col_kind[0][j] == dng::COL_P2) {
 					int e = 0;
 					if (v != v || std::isinf(v))
 						o = v;
@@ -103,7 +107,7 @@ int dng_result_from_points(const dng_plan *plan, size_t npoints,
 						o = e;
 					}
 				} else {
-					double q = v / r->col_step[j];
+					double q = v / r->col_step[0][j];
 					o = (q != q) ? q : std::floor(q) + 0.0;
 				}
 				uint64_t b;
@@ -118,7 +122,6 @@ int dng_result_from_points(const dng_plan *plan, size_t npoints,
 			}
 		}
 		rows.emplace_back(std::move(k), values[i]);
-		total += values[i];
 	}
 	std::sort(rows.begin(), rows.end());
 	for (auto &kv : rows) {
@@ -129,7 +132,7 @@ int dng_result_from_points(const dng_plan *plan, size_t npoints,
 			r->values.push_back(kv.second);
 		}
 	}
-	r->finalize(total);
+	r->finalize();
 	*out = r;
 	return DNG_OK;
 }
@@ -209,16 +212,15 @@ int dng_result_from_dense(const dng_result *like, const void *dict,
 	if (!dict_parse(dict, dictlen, keys) || keys.size() != n)
 		return DNG_EINVAL;
 	dng_result *r = new dng_result();
-	r->ncols = like->ncols;
+	r->nmetrics = like->nmetrics;
+	memcpy(r->ncols, like->ncols, sizeof (r->ncols));
 	memcpy(r->col_kind, like->col_kind, sizeof (r->col_kind));
 	memcpy(r->col_step, like->col_step, sizeof (r->col_step));
-	uint64_t total = 0;
 	for (size_t i = 0; i < n; i++) {
 		r->keys.push_back(keys[i]);
 		r->values.push_back(vec[i]);
-		total += vec[i];
 	}
-	r->finalize(total);
+	r->finalize();
 	*out = r;
 	return DNG_OK;
 }

@@ -800,95 +800,135 @@ struct Compiler {
 
 		std::vector<Leaf> prog;
 		P.ds_entry = (int16_t)compile_pred(root.get("ds_filter"), 0, prog);
-		P.user_entry = (int16_t)compile_pred(root.get("filter"), 0, prog);
 		if (this->code != DNG_OK)
 			return false;
 
-		const JVal *syn = root.get("synthetic");
-		if (syn && syn->k == JVal::ARR) {
-			if (syn->arr.size() > MAX_SYN)
-				return fail(DNG_ELIMIT, "too many synthetic fields");
-			for (auto &s : syn->arr) {
-				const JVal *n = s.get("name"), *f = s.get("field");
-				if (!n || !f || n->k != JVal::STR ||
-				    f->k != JVal::STR)
-					return fail(DNG_EINVAL, "synthetic: need "
-					    "string \"name\" and \"field\"");
-				int j = (int)syn_names.size();
-				P.syn[j] = resolve(f->str, j);
-				syn_names.push_back(n->str);
-			}
+		/* one metric (a plain scan: the plan object itself) or several
+		 * ("metrics": [...], the fan-out of dn build / index-scan) */
+		std::vector<const JVal *> mets;
+		const JVal *ml = root.get("metrics");
+		if (ml && ml->k == JVal::ARR) {
+			for (auto &m : ml->arr)
+				mets.push_back(&m);
+			if (mets.empty() || mets.size() > MAX_METRICS)
+				return fail(DNG_ELIMIT, "\"metrics\" must hold 1.."
+				    + std::to_string((int)MAX_METRICS) + " entries");
+		} else {
+			mets.push_back(&root);
 		}
-		P.nsyn = (u8)syn_names.size();
-
-		P.time_entry = -1;
-		const JVal *tb = root.get("time_bounds");
-		if (tb && tb->k == JVal::OBJ) {
-			const JVal *f = tb->get("field"), *ge = tb->get("ge"),
-			    *lt = tb->get("lt");
-			if (!f || f->k != JVal::STR || !ge || !lt ||
-			    ge->k != JVal::NUM || lt->k != JVal::NUM)
-				return fail(DNG_EINVAL, "time_bounds: need field, "
-				    "ge, lt");
-			/* {and:[{ge:[f,a]},{lt:[f,b]}]}: lib/dragnet-impl.js:108-119 */
-			P.time_entry = (int16_t)prog.size();
-			Leaf a, b;
-			memset(&a, 0, sizeof (a));
-			memset(&b, 0, sizeof (b));
-			a.op = OP_GE;
-			a.src = resolve(f->str, P.nsyn);
-			a.cnum = ge->num;
-			a.jt = (int16_t)(prog.size() + 1);
-			a.jf = -2;
-			b.op = OP_LT;
-			b.src = a.src;
-			b.cnum = lt->num;
-			b.jt = -1;
-			b.jf = -2;
-			prog.push_back(a);
-			prog.push_back(b);
-		}
-
-		const JVal *bds = root.get("breakdowns");
-		if (!bds || bds->k != JVal::ARR)
-			return fail(DNG_EINVAL, "plan: \"breakdowns\" must be an "
-			    "array");
-		if (bds->arr.size() > MAX_COLS)
-			return fail(DNG_ELIMIT, "too many breakdowns");
-		out->ncols = 0;
-		for (auto &b : bds->arr) {
-			const JVal *n = b.get("name");
-			if (!n || n->k != JVal::STR)
-				return fail(DNG_EINVAL, "breakdown without a name");
-			Col &c = P.col[P.ncols];
-			/* the aggregator plucks the breakdown NAME
-			 * (lib/dragnet-impl.js:79-80) */
-			c.src = resolve(n->str, P.nsyn);
-			c.kind = COL_DISCRETE;
-			c.step = 0;
-			const JVal *ag = b.get("aggr");
-			if (ag && ag->k == JVal::STR) {
-				if (ag->str == "quantize") {
-					c.kind = COL_P2;
-				} else if (ag->str == "lquantize") {
-					const JVal *st = b.get("step");
-					if (!st || st->k != JVal::NUM)
-						return fail(DNG_EINVAL, "aggr "
-						    "\"lquantize\" requires "
-						    "\"step\"");
-					c.kind = COL_LINEAR;
-					c.step = st->num;
-				} else {
-					return fail(DNG_EINVAL,
-					    "unsupported aggr: \"" + ag->str +
-					    "\"");
+		P.nmetrics = (u8)mets.size();
+		out->nmetrics = (int)mets.size();
+		int nsyn_total = 0, ncols_total = 0;
+		for (size_t mi = 0; mi < mets.size(); mi++) {
+			const JVal &mj = *mets[mi];
+			if (mj.k != JVal::OBJ)
+				return fail(DNG_EINVAL, "metric must be an object");
+			Metric &M = P.metric[mi];
+			/* synthetic names are private to a metric's StreamScan */
+			syn_names.assign((size_t)nsyn_total, std::string("\x01"));
+			M.user_entry = (int16_t)compile_pred(mj.get("filter"), 0,
+			    prog);
+			if (this->code != DNG_OK)
+				return false;
+			M.syn0 = (u8)nsyn_total;
+			const JVal *syn = mj.get("synthetic");
+			if (syn && syn->k == JVal::ARR) {
+				for (auto &sj : syn->arr) {
+					const JVal *n = sj.get("name"),
+					    *f = sj.get("field");
+					if (!n || !f || n->k != JVal::STR ||
+					    f->k != JVal::STR)
+						return fail(DNG_EINVAL, "synthetic: "
+						    "need string \"name\" and "
+						    "\"field\"");
+					if (nsyn_total >= MAX_SYN)
+						return fail(DNG_ELIMIT, "too many "
+						    "synthetic fields");
+					P.syn[nsyn_total] = resolve(f->str,
+					    nsyn_total);
+					syn_names.push_back(n->str);
+					nsyn_total++;
 				}
 			}
-			out->col_kind[P.ncols] = c.kind;
-			out->col_step[P.ncols] = c.step;
-			P.ncols++;
+			M.nsyn = (u8)(nsyn_total - M.syn0);
+
+			M.time_entry = -1;
+			const JVal *tb = mj.get("time_bounds");
+			if (tb && tb->k == JVal::OBJ) {
+				const JVal *f = tb->get("field"), *ge = tb->get("ge"),
+				    *lt = tb->get("lt");
+				if (!f || f->k != JVal::STR || !ge || !lt ||
+				    ge->k != JVal::NUM || lt->k != JVal::NUM)
+					return fail(DNG_EINVAL, "time_bounds: need "
+					    "field, ge, lt");
+				/* {and:[{ge:[f,a]},{lt:[f,b]}]}:
+				 * lib/dragnet-impl.js:108-119 */
+				M.time_entry = (int16_t)prog.size();
+				Leaf a, b;
+				memset(&a, 0, sizeof (a));
+				memset(&b, 0, sizeof (b));
+				a.op = OP_GE;
+				a.src = resolve(f->str, nsyn_total);
+				a.cnum = ge->num;
+				a.jt = (int16_t)(prog.size() + 1);
+				a.jf = -2;
+				b.op = OP_LT;
+				b.src = a.src;
+				b.cnum = lt->num;
+				b.jt = -1;
+				b.jf = -2;
+				prog.push_back(a);
+				prog.push_back(b);
+			}
+
+			const JVal *bds = mj.get("breakdowns");
+			if (!bds || bds->k != JVal::ARR)
+				return fail(DNG_EINVAL, "plan: \"breakdowns\" must "
+				    "be an array");
+			if (bds->arr.size() > 12)
+				return fail(DNG_ELIMIT, "too many breakdowns");
+			M.col0 = (u8)ncols_total;
+			int nc = 0;
+			for (auto &bj : bds->arr) {
+				const JVal *n = bj.get("name");
+				if (!n || n->k != JVal::STR)
+					return fail(DNG_EINVAL, "breakdown without "
+					    "a name");
+				if (ncols_total >= MAX_COLS)
+					return fail(DNG_ELIMIT, "too many "
+					    "breakdown columns in one scan");
+				Col &c = P.col[ncols_total];
+				/* the aggregator plucks the breakdown NAME
+				 * (lib/dragnet-impl.js:79-80) */
+				c.src = resolve(n->str, nsyn_total);
+				c.kind = COL_DISCRETE;
+				c.step = 0;
+				const JVal *ag = bj.get("aggr");
+				if (ag && ag->k == JVal::STR) {
+					if (ag->str == "quantize") {
+						c.kind = COL_P2;
+					} else if (ag->str == "lquantize") {
+						const JVal *st = bj.get("step");
+						if (!st || st->k != JVal::NUM)
+							return fail(DNG_EINVAL,
+							    "aggr \"lquantize\" "
+							    "requires \"step\"");
+						c.kind = COL_LINEAR;
+						c.step = st->num;
+					} else {
+						return fail(DNG_EINVAL,
+						    "unsupported aggr: \"" +
+						    ag->str + "\"");
+					}
+				}
+				out->col_kind[mi][nc] = c.kind;
+				out->col_step[mi][nc] = c.step;
+				nc++;
+				ncols_total++;
+			}
+			M.ncols = (u8)nc;
+			out->ncols[mi] = nc;
 		}
-		out->ncols = P.ncols;
 		if (this->code != DNG_OK)
 			return false;
 

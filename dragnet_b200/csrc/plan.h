@@ -39,7 +39,8 @@ enum : u8 {
 
 enum : int {
 	MAX_SLOTS = 32, MAX_CTX = 24, MAX_CANDS = 64, MAX_PATHS = 24,
-	MAX_LEVELS = 8, MAX_CODE = 48, MAX_SYN = 8, MAX_COLS = 12,
+	MAX_LEVELS = 8, MAX_CODE = 48, MAX_SYN = 12, MAX_COLS = 16,
+	MAX_METRICS = 8,
 	POOL_BYTES = 2048, KEY_MAX = 512
 };
 
@@ -132,6 +133,18 @@ struct FastTab {
 	u8 pad[3];
 };
 
+/*
+ * One metric = one StreamScan of the reference (lib/stream-scan.js:40-94): user
+ * filter, its synthetic date fields, time bounds, breakdown columns.  A plain
+ * `dn scan` has one; `dn build` / index-scan fans one parsed record out to
+ * several (lib/datasource-file.js:386-432).
+ */
+struct Metric {
+	int16_t user_entry, time_entry;		/* -1 none */
+	u8 syn0, nsyn;				/* range in DevPlan::syn */
+	u8 col0, ncols;				/* range in DevPlan::col */
+};
+
 struct DevPlan {
 	Leaf code[MAX_CODE];
 	Col col[MAX_COLS];
@@ -139,9 +152,11 @@ struct DevPlan {
 	Cand cand[MAX_CANDS];
 	PathInfo path[MAX_PATHS];
 	Src syn[MAX_SYN];
-	int16_t ds_entry, user_entry, time_entry;	/* -1 none */
+	Metric metric[MAX_METRICS];
+	int16_t ds_entry;		/* datasource filter, -1 none */
 	u8 format;
-	u8 nctx, ncand, npaths, nslots, nsyn, ncols, ncode;
+	u8 nmetrics;
+	u8 nctx, ncand, npaths, nslots, ncode;
 	int8_t root_ctx;	/* context of the record's fields object */
 	int8_t sk_fields_slot, sk_value_slot;	/* json-skinner envelope */
 	u8 pad[3];
@@ -165,10 +180,11 @@ static inline u32 devplan_smem_bytes(const DevPlan &p)
 
 struct dng_plan {
 	dng::DevPlan dev;
-	/* host copies for result rendering */
-	int ncols;
-	dng::u8 col_kind[dng::MAX_COLS];
-	double col_step[dng::MAX_COLS];
+	/* host copies for result rendering, per metric */
+	int nmetrics;
+	int ncols[dng::MAX_METRICS];
+	dng::u8 col_kind[dng::MAX_METRICS][dng::MAX_COLS];
+	double col_step[dng::MAX_METRICS][dng::MAX_COLS];
 };
 
 /* host-only: compile plan JSON. Returns 0 or DNG_E*, message in err. */

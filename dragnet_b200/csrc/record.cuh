@@ -1046,18 +1046,15 @@ DNG_HD double linear_ordinal(double x, double step)
 }
 
 /*
- * Run the stages after JSON decode on one parsed record.  Returns 1 when the
- * record reaches the aggregator; then kbuf[0..klen) is its encoded group key
- * (per column: u16 len + bytes, or 0xFFFF + 8 bytes of ordinal) zero-padded
- * to a multiple of 8, and weight its value.
+ * Stages shared by every metric of a record: the json-skinner envelope and the
+ * datasource filter (lib/datasource-file.js:154-163 puts it on the parser, in
+ * front of all StreamScans).  Returns 1 if the record goes on.
  */
-DNG_HD int process_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R,
-    LocalCounters &C, u8 *kbuf, u32 &klen, u64 &weight)
+DNG_HD int prepare_record(const u8 *rec, const DevPlan &P, RecState &R,
+    LocalCounters &C, u8 *kbuf, u64 &weight)
 {
-	(void)len;
 	u32 ovf = 0, slow = 0;
 	weight = 1;
-	klen = 0;
 	if (P.format == FMT_SKINNER) {
 		/* the line is a point {fields:{..}, value:N}
 		 * (lib/format-json.js:55-73); anything else is dropped */
@@ -1077,17 +1074,36 @@ DNG_HD int process_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R,
 	}
 	if (P.ds_entry >= 0) {
 		int r = eval_program(rec, P, R, P.ds_entry, kbuf, ovf, slow);
+		if (ovf)
+			C.unsupported++;
 		if (r < 0) {
 			C.ds_failedeval++;
-			goto dropped;
+			return 0;
 		}
 		if (!r) {
 			C.ds_filtered++;
-			goto dropped;
+			return 0;
 		}
 	}
-	if (P.user_entry >= 0) {
-		int r = eval_program(rec, P, R, P.user_entry, kbuf, ovf, slow);
+	return 1;
+}
+
+/*
+ * One metric's StreamScan on a prepared record: user filter -> synthetic
+ * dates -> time bounds -> group key (lib/stream-scan.js:56-86).  Returns 1
+ * when the record reaches the aggregator; then kbuf[0..klen) is its encoded
+ * group key -- [0xFD, metric] when the plan fans out to several metrics, then
+ * per column u16 len + bytes, or 0xFFFF + 8 bytes of ordinal -- zero padded to
+ * a multiple of 8.
+ */
+DNG_HD int process_metric(const u8 *rec, const DevPlan &P, u32 mi, RecState &R,
+    LocalCounters &C, u8 *kbuf, u32 &klen)
+{
+	const Metric &M = P.metric[mi];
+	u32 ovf = 0, slow = 0;
+	klen = 0;
+	if (M.user_entry >= 0) {
+		int r = eval_program(rec, P, R, M.user_entry, kbuf, ovf, slow);
 		if (r < 0) {
 			C.user_failedeval++;
 			goto dropped;
@@ -1097,9 +1113,9 @@ DNG_HD int process_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R,
 			goto dropped;
 		}
 	}
-	if (P.nsyn) {
+	if (M.nsyn) {
 		u32 nerr = 0;
-		for (u32 j = 0; j < P.nsyn; j++) {
+		for (u32 j = M.syn0; j < (u32)M.syn0 + M.nsyn; j++) {
 			V v = get_src(P, R, P.syn[j]);
 			u32 t = val_type(v.pk);
 			if (t == T_UNDEF) {
@@ -1136,8 +1152,8 @@ DNG_HD int process_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R,
 		if (nerr)
 			goto dropped;
 	}
-	if (P.time_entry >= 0) {
-		int r = eval_program(rec, P, R, P.time_entry, kbuf, ovf, slow);
+	if (M.time_entry >= 0) {
+		int r = eval_program(rec, P, R, M.time_entry, kbuf, ovf, slow);
 		if (r < 0) {
 			C.time_failedeval++;
 			goto dropped;
@@ -1149,7 +1165,12 @@ DNG_HD int process_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R,
 	}
 	{
 		u32 o = 0;
-		for (u32 j = 0; j < P.ncols; j++) {
+		if (P.nmetrics > 1) {
+			kbuf[0] = 0xFD;
+			kbuf[1] = (u8)mi;
+			o = 2;
+		}
+		for (u32 j = M.col0; j < (u32)M.col0 + M.ncols; j++) {
 			const Col &col = P.col[j];
 			V v = get_src(P, R, col.src);
 			if (o + 10 > KEY_MAX) {

@@ -17,20 +17,23 @@
 #include "plan.h"
 
 struct dng_result {
-	int ncols = 0;
-	dng::u8 col_kind[dng::MAX_COLS];
-	double col_step[dng::MAX_COLS];
+	int nmetrics = 1;
+	int ncols[dng::MAX_METRICS] = {};
+	dng::u8 col_kind[dng::MAX_METRICS][dng::MAX_COLS];
+	double col_step[dng::MAX_METRICS][dng::MAX_COLS];
 	/* sorted by encoded key */
 	std::vector<std::string> keys;
 	std::vector<uint64_t> values;
 	/* decoded columns, filled by finalize() */
 	struct Cell { size_t off, len; double num; uint8_t is_number; };
-	std::vector<Cell> cells;	/* keys.size() * ncols */
+	std::vector<Cell> cells;	/* point i: cells[cell0[i] ...] */
+	std::vector<size_t> cell0;
+	std::vector<int> metric;	/* metric of point i */
 	std::string dict;		/* serialised dictionary (lazy) */
 
 	void init_from_plan(const dng_plan *p);
 	/* sort, apply the "no breakdowns => exactly one point" rule, decode */
-	void finalize(uint64_t total_if_no_cols);
+	void finalize();
 };
 
 double dng_bucket_min(dng::u8 kind, double step, double ordinal);

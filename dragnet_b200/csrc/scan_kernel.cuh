@@ -49,7 +49,7 @@ namespace dng {
 #define DNG_SKEY 40			/* inline key bytes per shared slot */
 #define DNG_MAXREC (1u << 24)		/* longest line handled */
 
-enum { NCTR = 24 };
+enum { NCTR = 24, MCTR_PER = 8 };	/* + (MAX_METRICS-1) x MCTR_PER for fan-out */
 enum {
 	CTR_LINES = 0, CTR_INVALID_JSON, CTR_INVALID_POINT,
 	CTR_DS_FILTERED, CTR_DS_FAILED, CTR_USER_FILTERED, CTR_USER_FAILED,
@@ -313,24 +313,61 @@ __device__ __forceinline__ u32 byte_range_mask(u32 p, u32 lo, u32 hi)
 
 /* ---- one record ----------------------------------------------------------- */
 
+/*
+ * Fan-out (dn build / index-scan): the further metrics of an already parsed
+ * and prepared record.  Out of line so that the single-metric path stays lean;
+ * stage counters of metrics >= 1 go to per-CTA shared counters.
+ */
+__device__ __noinline__ void scan_tail_fanout(const u8 *rec, const DevPlan &P,
+    RecState &R, SSlot *stab, const GTable &gt, LocalCounters &C, u32 *mctr,
+    u64 w)
+{
+	__align__(8) u8 kbuf[KEY_MAX + 16];
+	const unsigned long long *kw = (const unsigned long long *)kbuf;
+	u32 klen;
+	for (u32 mi = 1; mi < P.nmetrics; mi++) {
+		LocalCounters T;
+		T.user_filtered = T.user_failedeval = T.synth_undef = 0;
+		T.synth_baddate = T.time_filtered = T.time_failedeval = 0;
+		T.aggr = T.slow = T.unsupported = 0;
+		if (process_metric(rec, P, mi, R, T, kbuf, klen))
+			shared_add(stab, gt, key_hash_words(kw, klen), kw, klen,
+			    w);
+		u32 *mc = mctr + (mi - 1) * MCTR_PER;
+		if (T.user_filtered) atomicAdd(&mc[0], 1u);
+		if (T.user_failedeval) atomicAdd(&mc[1], 1u);
+		if (T.synth_undef) atomicAdd(&mc[2], 1u);
+		if (T.synth_baddate) atomicAdd(&mc[3], 1u);
+		if (T.time_filtered) atomicAdd(&mc[4], 1u);
+		if (T.time_failedeval) atomicAdd(&mc[5], 1u);
+		if (T.aggr) atomicAdd(&mc[6], 1u);
+		C.slow += T.slow;
+		C.unsupported += T.unsupported;
+	}
+}
+
 /* stages after JSON decode + aggregation, for a parsed record */
 __device__ __forceinline__ void scan_tail(const u8 *rec, u32 len,
     const DevPlan &P, RecState &R, SSlot *stab, const GTable &gt,
-    LocalCounters &C)
+    LocalCounters &C, u32 *mctr)
 {
+	(void)len;
 	__align__(8) u8 kbuf[KEY_MAX + 16];
 	u32 klen;
 	u64 w;
-	if (process_record(rec, len, P, R, C, kbuf, klen, w)) {
-		const unsigned long long *kw = (const unsigned long long *)kbuf;
-		u64 h = key_hash_words(kw, klen);
-		shared_add(stab, gt, h, kw, klen, w);
-	}
+	if (!prepare_record(rec, P, R, C, kbuf, w))
+		return;
+	const unsigned long long *kw = (const unsigned long long *)kbuf;
+	if (process_metric(rec, P, 0, R, C, kbuf, klen))
+		shared_add(stab, gt, key_hash_words(kw, klen), kw, klen, w);
+	if (P.nmetrics > 1)
+		scan_tail_fanout(rec, P, R, stab, gt, C, mctr, w);
 }
 
 /* general (branchy, exact for everything) path */
 __device__ __forceinline__ void scan_one(const u8 *rec, u32 len,
-    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C)
+    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C,
+    u32 *mctr)
 {
 	RecState R;
 	C.lines++;
@@ -345,21 +382,23 @@ __device__ __forceinline__ void scan_one(const u8 *rec, u32 len,
 		C.invalid_json++;
 		return;
 	}
-	scan_tail(rec, len, P, R, stab, gt, C);
+	scan_tail(rec, len, P, R, stab, gt, C, mctr);
 }
 
 __device__ __noinline__ void scan_one_shared(const u8 *rec, u32 len,
-    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C)
+    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C,
+    u32 *mctr)
 {
-	scan_one(rec, len, P, stab, gt, C);
+	scan_one(rec, len, P, stab, gt, C, mctr);
 }
 
 /* out-of-line copy for lines that begin before the staged window (rare):
  * keeps the hot shared-memory instantiation of the parser small */
 __device__ __noinline__ void scan_one_global(const u8 *rec, u32 len,
-    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C)
+    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C,
+    u32 *mctr)
 {
-	scan_one(rec, len, P, stab, gt, C);
+	scan_one(rec, len, P, stab, gt, C, mctr);
 }
 
 /* ---- the kernel ------------------------------------------------------------ */
@@ -376,6 +415,7 @@ scan_kernel(const ScanArgs a)
 	__shared__ u32 wsum[DNG_NT / 32];
 	__shared__ u32 s_total;
 	__shared__ u32 s_prev;		/* newline before the current pass */
+	__shared__ u32 s_mctr[(MAX_METRICS - 1) * MCTR_PER];
 
 	const u32 tid = threadIdx.x;
 	const u32 lane = tid & 31, wid = tid >> 5;
@@ -391,6 +431,8 @@ scan_kernel(const ScanArgs a)
 			tz[i] = z;
 		if (tid == 0)
 			mbar_init(&mbar, 1);
+		if (tid < (MAX_METRICS - 1) * MCTR_PER)
+			s_mctr[tid] = 0;
 	}
 	__syncthreads();
 	const DevPlan &P = *sp;
@@ -607,13 +649,14 @@ scan_kernel(const ScanArgs a)
 				if (fast && fs.state == FS_FIN) {
 					C.lines++;
 					fast_finish(rec, fs, R);
-					scan_tail(rec, len, P, R, stab, a.tab, C);
+					scan_tail(rec, len, P, R, stab, a.tab, C,
+					    s_mctr);
 				} else if (fast && fs.state == FS_ERR) {
 					C.lines++;
 					C.invalid_json++;
 				} else if (have && !islong) {
 					scan_one_shared(sdata + beg, len, P, stab,
-					    a.tab, C);
+					    a.tab, C, s_mctr);
 				} else if (have) {
 					/* the line began before the staged
 					 * window: find its start in HBM and
@@ -626,7 +669,7 @@ scan_kernel(const ScanArgs a)
 					scan_one_global(a.data + q,
 					    (u32)min((unsigned long long)
 					    DNG_MAXREC, ws + end - q), P, stab,
-					    a.tab, C);
+					    a.tab, C, s_mctr);
 				}
 			}
 			__syncthreads();
@@ -650,6 +693,10 @@ scan_kernel(const ScanArgs a)
 			    s->count_lo);
 		}
 	}
+
+	if (tid < (MAX_METRICS - 1) * MCTR_PER && s_mctr[tid])
+		atomicAdd(&a.counters[NCTR + tid],
+		    (unsigned long long)s_mctr[tid]);
 
 	/* counters: warp reduce, one atomic per warp per counter */
 	u32 vals[NCTR];

@@ -94,6 +94,22 @@ def run_plan(plan, files=(), chunks=None, device=0, device_buffers=None):
         flat = s.counters()
         stats = s.kernel_stats()
         pts = []
+        if 'metrics' in plan:
+            # fan-out: points are tagged like the reference tags them
+            # (fields.__dn_metric = qi, lib/datasource-file.js:412-419)
+            mflat = [s.counters(m) for m in range(len(plan['metrics']))]
+            for m, cols, value in res.points(with_metric=True):
+                names = [b['name'] for b in plan['metrics'][m]['breakdowns']]
+                pts.append((list(zip(names, cols)) + [('__dn_metric', m)],
+                            value))
+            res.close()
+            counters = []
+            for m, mp in enumerate(plan['metrics']):
+                one = dict(mp, format=plan.get('format', 'json'),
+                           ds_filter=plan.get('ds_filter'))
+                npts = sum(1 for f, _ in pts if f[-1][1] == m)
+                counters.append(stage_counters(one, mflat[m], npts))
+            return ScanResult(pts, counters, list(files), mflat, stats)
         names = [b['name'] for b in plan['breakdowns']]
         for cols, value in res.points():
             pts.append((list(zip(names, cols)), value))
@@ -140,10 +156,34 @@ class DatasourceGpu(object):
                                    data_format=self.ds_format)
         return run_plan(plan, files=files, device=self.ds_device)
 
-    def build(self, *a, **k):
-        raise NotImplementedError('index build stays on the reference path')
+    def indexScan(self, args):
+        """The scan half of build/index-scan (lib/datasource-file.js:321-433):
+        one pass over the raw data computing every metric; returns the points
+        an IndexSink would store, each tagged ('__dn_metric', i).  args:
+        metrics [{'filter', 'breakdowns'}], interval, dryRun, timeAfter,
+        timeBefore (ms)."""
+        after, before = args.get('timeAfter'), args.get('timeBefore')
+        if self.ds_timefield is None and (args['interval'] != 'all' or
+                                          after or before):
+            return DsError('datasource is missing "timefield"')
+        files = mod_find.find_files(self.ds_datapath, self.ds_timeformat,
+                                    after, before)
+        if args.get('dryRun'):
+            return ScanResult([], {}, files)
+        queries = [mod_query.metricQuery(m, after, before, args['interval'],
+                                         self.ds_timefield)
+                   for m in args['metrics']]
+        plan = mod_query.scan_plan_multi(queries, ds_filter=self.ds_filter,
+                                         time_field=self.ds_timefield,
+                                         data_format=self.ds_format)
+        return run_plan(plan, files=files, device=self.ds_device)
 
-    query = indexScan = indexRead = build
+    def build(self, *a, **k):
+        raise NotImplementedError('writing sqlite indexes stays on the '
+                                  'reference path (IndexSink); use indexScan '
+                                  'for the points')
+
+    query = indexRead = build
 
 
 def createDatasource(args):

@@ -63,6 +63,8 @@ _SIGS = [
     ('dng_scan_sync', ctypes.c_int, [_P]),
     ('dng_scan_finish', ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     ('dng_scan_counters', ctypes.c_int, [_P, ctypes.POINTER(DngCounters)]),
+    ('dng_scan_counters_metric', ctypes.c_int,
+     [_P, ctypes.c_int, ctypes.POINTER(DngCounters)]),
     ('dng_scan_error', ctypes.c_char_p, [_P]),
     ('dng_scan_destroy', None, [_P]),
     ('dng_scan_kernel_stats', ctypes.c_int,
@@ -72,6 +74,9 @@ _SIGS = [
     ('dng_pinned_free', None, [_P]),
     ('dng_result_count', ctypes.c_size_t, [_P]),
     ('dng_result_ncols', ctypes.c_size_t, [_P]),
+    ('dng_result_nmetrics', ctypes.c_size_t, [_P]),
+    ('dng_result_ncols_metric', ctypes.c_size_t, [_P, ctypes.c_int]),
+    ('dng_result_metric', ctypes.c_int, [_P, ctypes.c_size_t]),
     ('dng_result_get', ctypes.c_int,
      [_P, ctypes.c_size_t, ctypes.POINTER(ctypes.c_char_p),
       ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_uint8),
@@ -167,7 +172,9 @@ class Result(object):
     def __init__(self, handle):
         self.handle = handle
 
-    def points(self):
+    def points(self, with_metric=False):
+        """[([col, ...], value)]; with_metric=True -> [(metric, cols, value)]
+        for fan-out plans."""
         L = lib()
         n = L.dng_result_count(self.handle)
         nc = L.dng_result_ncols(self.handle)
@@ -182,13 +189,17 @@ class Result(object):
             _check(L.dng_result_get(self.handle, i, strs, lens, isnum, nums,
                                     ctypes.byref(val)))
             cols = []
-            for j in range(nc):
+            m = L.dng_result_metric(self.handle, i)
+            for j in range(L.dng_result_ncols_metric(self.handle, m)):
                 if isnum[j]:
                     cols.append(float(nums[j]))
                 else:
                     cols.append(ctypes.string_at(ptrs[j], lens[j])
                                 if lens[j] else b'')
-            out.append((cols, int(val.value)))
+            if with_metric:
+                out.append((m, cols, int(val.value)))
+            else:
+                out.append((cols, int(val.value)))
         return out
 
     def dict_bytes(self):
@@ -303,10 +314,10 @@ class Scan(object):
                self.handle)
         return Result(out)
 
-    def counters(self):
+    def counters(self, metric=0):
         c = DngCounters()
-        _check(lib().dng_scan_counters(self.handle, ctypes.byref(c)),
-               self.handle)
+        _check(lib().dng_scan_counters_metric(self.handle, metric,
+                                              ctypes.byref(c)), self.handle)
         return c.as_dict()
 
     def kernel_stats(self):

@@ -277,5 +277,42 @@ def scan_plan(query, ds_filter=None, time_field=None, data_format='json'):
     }
 
 
+def metricQuery(metric, after, before, interval, timefield):
+    """lib/dragnet-impl.js:290-323: the query that computes one metric of an
+    index; unless interval is 'all' a `__dn_ts[lquantize, step, date]`
+    breakdown is prepended.  ``metric`` = {'filter', 'breakdowns': [...]}
+    (config form: name/field[/date/aggr/step])."""
+    qconf = {'filter': metric.get('filter'),
+             'breakdowns': copy.deepcopy(metric.get('breakdowns') or [])}
+    if interval != 'all':
+        step = {'hour': 3600, 'day': 86400}[interval]
+        qconf['breakdowns'].insert(0, {
+            'name': '__dn_ts', 'aggr': 'lquantize', 'step': step,
+            'field': timefield, 'date': ''})
+    if after:
+        qconf['timeAfter'] = after
+    if before:
+        qconf['timeBefore'] = before
+    q = queryLoad({'allowReserved': True, 'query': qconf})
+    assert not isinstance(q, Exception), q
+    return q
+
+
+def scan_plan_multi(queries, ds_filter=None, time_field=None,
+                    data_format='json'):
+    """One pass, several metrics: what DatasourceFile.indexScanImpl wires up
+    (lib/datasource-file.js:386-432): the datasource filter sits on the
+    parser, every metric gets its own StreamScan."""
+    metrics = []
+    for q in queries:
+        p = scan_plan(q, ds_filter=None, time_field=time_field,
+                      data_format=data_format)
+        metrics.append({'filter': p['filter'], 'synthetic': p['synthetic'],
+                        'time_bounds': p['time_bounds'],
+                        'breakdowns': p['breakdowns']})
+    return {'format': data_format, 'ds_filter': ds_filter or None,
+            'metrics': metrics}
+
+
 def scan_plan_json(*args, **kwargs):
     return json.dumps(scan_plan(*args, **kwargs), separators=(',', ':'))

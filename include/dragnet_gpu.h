@@ -91,6 +91,9 @@ typedef struct dng_counters {
  *     "time_bounds": { "field": "dn_ts", "ge": sec, "lt": sec } | null,
  *     "breakdowns": [ { "name": s, "field": s, ["date": true,]
  *                       ["aggr": "quantize" | "lquantize", "step": n] }, ... ] }
+ * or, to scan several metrics in one pass over the data (dn build):
+ *   { "format": ..., "ds_filter": ...,
+ *     "metrics": [ { "filter", "synthetic", "time_bounds", "breakdowns" }, ... ] }
  */
 int dng_plan_create(const char *plan_json, dng_plan **out,
     char *err, size_t errlen);
@@ -129,6 +132,8 @@ int dng_scan_sync(dng_scan *scan);
 /* End of input: flushes the final unterminated line, then emits the points. */
 int dng_scan_finish(dng_scan *scan, dng_result **out);
 int dng_scan_counters(dng_scan *scan, dng_counters *out);
+/* counters of metric m's StreamScan (m = 0 is what dng_scan_counters gives) */
+int dng_scan_counters_metric(dng_scan *scan, int metric, dng_counters *out);
 const char *dng_scan_error(const dng_scan *scan);
 void dng_scan_destroy(dng_scan *scan);
 
@@ -151,6 +156,12 @@ void dng_pinned_free(void *p);
  */
 size_t dng_result_count(const dng_result *r);
 size_t dng_result_ncols(const dng_result *r);
+/* Fan-out plans ("metrics": [...], the reference's dn build / index-scan,
+ * lib/datasource-file.js:386-432): every point belongs to one metric (the
+ * reference tags it fields.__dn_metric) and has that metric's columns. */
+size_t dng_result_nmetrics(const dng_result *r);
+size_t dng_result_ncols_metric(const dng_result *r, int metric);
+int dng_result_metric(const dng_result *r, size_t i);
 int dng_result_get(const dng_result *r, size_t i, const char **strs,
     size_t *strlens, uint8_t *is_number, double *numvals, uint64_t *value);
 void dng_result_destroy(dng_result *r);

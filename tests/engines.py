@@ -137,6 +137,40 @@ def hostcheck_engine(plan, files):
     return points, staged_counters(plan, doc['counters'], len(points))
 
 
+def hostcheck_multi(plan, files, fast=False):
+    """Fan-out plan through the host build of the device logic ->
+    ({metric: canon points}, [flat drop counters per metric])."""
+    exe = build_hostcheck()
+    with tempfile.NamedTemporaryFile('w', suffix='.json', delete=False) as f:
+        json.dump(plan, f)
+        pf = f.name
+    env = dict(os.environ)
+    env.pop('DNG_HOSTCHECK_FAST', None)
+    if fast:
+        env['DNG_HOSTCHECK_FAST'] = '1'
+    try:
+        out = subprocess.run([exe, pf] + list(files), capture_output=True,
+                             check=True, env=env).stdout
+    finally:
+        os.unlink(pf)
+    doc = json.loads(out)
+    assert doc['counters']['unsupported'] == 0
+    per = {}
+    for p in doc['points']:
+        m = p['metric']
+        bds = plan['metrics'][m]['breakdowns']
+        fields = []
+        for b, col in zip(bds, p['cols']):
+            if 's' in col:
+                fields.append((b['name'], bytes.fromhex(col['s'])))
+            else:
+                fields.append((b['name'], struct.unpack(
+                    '<d', struct.pack('<Q', int(col['n'], 16)))[0]))
+        per.setdefault(m, []).append((fields, p['value']))
+    flats = [doc['counters']] + doc['mcounters']
+    return per, flats
+
+
 def build_cpp_oracle():
     subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle')])
     return os.path.join(ROOT, 'oracle', 'dn_oracle_cpp')

@@ -52,8 +52,9 @@ int main(int argc, char **argv)
 	memset(&C, 0, sizeof (C));
 	bool use_fast = getenv("DNG_HOSTCHECK_FAST") != nullptr;
 	unsigned long nfast = 0;
+	static LocalCounters MCs[MAX_METRICS];
+	memset(MCs, 0, sizeof (MCs));
 	std::map<std::string, uint64_t> table;
-	uint64_t total = 0;
 	static RecState R;
 	static u8 kbuf[KEY_MAX + 64];
 	size_t pos = 0;
@@ -94,10 +95,15 @@ int main(int argc, char **argv)
 		} else {
 			u32 klen;
 			u64 w;
-			if (process_record(rec, len, plan.dev, R, C, kbuf, klen,
-			    w)) {
-				table[std::string((char *)kbuf, klen)] += w;
-				total += w;
+			if (prepare_record(rec, plan.dev, R, C, kbuf, w)) {
+				for (u32 mi = 0; mi < plan.dev.nmetrics; mi++) {
+					LocalCounters &MC = mi ? MCs[mi] : C;
+					if (process_metric(rec, plan.dev, mi, R, MC,
+					    kbuf, klen)) {
+						table[std::string((char *)kbuf,
+						    klen)] += w;
+					}
+				}
 			}
 		}
 		pos = end + 1;
@@ -108,12 +114,12 @@ int main(int argc, char **argv)
 		res.keys.push_back(kv.first);
 		res.values.push_back(kv.second);
 	}
-	res.finalize(total);
+	res.finalize();
 	printf("{\"points\":[");
 	for (size_t i = 0; i < res.keys.size(); i++) {
-		printf("%s{\"cols\":[", i ? "," : "");
-		for (int j = 0; j < res.ncols; j++) {
-			const dng_result::Cell &c = res.cells[i * res.ncols + j];
+		printf("%s{\"metric\":%d,\"cols\":[", i ? "," : "", res.metric[i]);
+		for (int j = 0; j < res.ncols[res.metric[i]]; j++) {
+			const dng_result::Cell &c = res.cells[res.cell0[i] + j];
 			if (j)
 				printf(",");
 			if (c.is_number) {
@@ -137,6 +143,17 @@ int main(int argc, char **argv)
 	CTR(ds_failedeval); CTR(user_filtered); CTR(user_failedeval);
 	CTR(synth_undef); CTR(synth_baddate); CTR(time_filtered);
 	CTR(time_failedeval); CTR(aggr); CTR(slow);
-	printf("\"unsupported\":%u},\"nfast\":%lu}\n", C.unsupported, nfast);
+	printf("\"unsupported\":%u},\"mcounters\":[", C.unsupported);
+	for (u32 mi = 1; mi < plan.dev.nmetrics; mi++) {
+		const LocalCounters &M = MCs[mi];
+		printf("%s{\"user_filtered\":%u,\"user_failedeval\":%u,"
+		    "\"synth_undef\":%u,\"synth_baddate\":%u,"
+		    "\"time_filtered\":%u,\"time_failedeval\":%u,\"aggr\":%u}",
+		    mi > 1 ? "," : "", M.user_filtered, M.user_failedeval,
+		    M.synth_undef, M.synth_baddate, M.time_filtered,
+		    M.time_failedeval, M.aggr);
+		C.unsupported += M.unsupported;
+	}
+	printf("],\"nfast\":%lu}\n", nfast);
 	return 0;
 }
