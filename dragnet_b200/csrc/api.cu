@@ -58,7 +58,7 @@ struct dng_scan {
 	dng_plan plan;
 	int device = 0;
 	int sm_count = 0;
-	u32 plan_bytes = 0;
+	u32 plan_bytes = 0, sslots = 0, s1slots = 0;
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
 	cudaStream_t own_stream = nullptr;
 	DevPlan *d_plan = nullptr;
@@ -136,10 +136,14 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 	a.ntiles = (u32)((nbytes + DNG_TILE - 1) / DNG_TILE);
 	a.final = final ? 1 : 0;
 	a.plan_bytes = s->plan_bytes;
+	a.sslots = s->sslots;
+	a.s1slots = s->s1slots;
 	u32 grid = std::min<u32>(a.ntiles, (u32)s->sm_count * DNG_CTAS_PER_SM);
 	cudaEvent_t e0 = get_event(s), e1 = get_event(s);
 	cudaEventRecord(e0, s->stream);
-	scan_kernel<<<grid, DNG_NT, SMEM_FIXED + s->plan_bytes, s->stream>>>(a);
+	scan_kernel<<<grid, DNG_NT, SMEM_FIXED + s->plan_bytes +
+	    s->sslots * sizeof (SSlot) + s->s1slots * sizeof (SSlot1),
+	    s->stream>>>(a);
 	cudaEventRecord(e1, s->stream);
 	s->ev_pairs.emplace_back(e0, e1);
 	s->launches++;
@@ -293,11 +297,36 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 			break;
 		s->sm_count = prop.multiProcessorCount;
 		s->plan_bytes = devplan_smem_bytes(plan->dev);
+		{
+			/* the tally cache takes whatever shared memory is left
+			 * when two CTAs share an SM (1 KB is reserved per CTA) */
+			size_t per_cta = prop.sharedMemPerMultiprocessor /
+			    DNG_CTAS_PER_SM - 1024 - 256;
+			size_t used = SMEM_FIXED + s->plan_bytes;
+			size_t room = per_cta > used ? per_cta - used : 0;
+			/* tier 1: 128 inline-key slots (64 when tight); tier 2:
+			 * as many compact slots as still fit (power of two) */
+			s->s1slots = room >= 24576 ? 256 : room >= 12288 ? 128 : 64;
+			size_t t1 = (size_t)s->s1slots * sizeof (SSlot1);
+			size_t left = room > t1 ? room - t1 : 0;
+			u32 n = DNG_SSLOTS_MIN;
+			while (n * 2 <= DNG_SSLOTS_MAX &&
+			    (size_t)n * 2 * sizeof (SSlot) <= left)
+				n *= 2;
+			s->sslots = n;
+		}
 		if ((rc = s->cuda(cudaFuncSetAttribute(scan_kernel,
 		    cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    (int)(SMEM_FIXED + sizeof (DevPlan))),
+		    (int)prop.sharedMemPerBlockOptin - 1024),
 		    "cudaFuncSetAttribute")))
 			break;
+		if (SMEM_FIXED + s->plan_bytes + s->sslots * sizeof (SSlot) +
+		    s->s1slots * sizeof (SSlot1) >
+		    prop.sharedMemPerBlockOptin - 1024) {
+			rc = s->fail(DNG_ELIMIT, "plan does not fit in shared "
+			    "memory");
+			break;
+		}
 		if ((rc = s->cuda(cudaStreamCreateWithFlags(&s->stream,
 		    cudaStreamNonBlocking), "cudaStreamCreate")))
 			break;
@@ -305,7 +334,7 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		if ((rc = s->cuda(cudaStreamCreateWithFlags(&s->copy_stream,
 		    cudaStreamNonBlocking), "cudaStreamCreate")))
 			break;
-		if ((rc = s->cuda(cudaMalloc(&s->d_plan, sizeof (DevPlan)),
+		if ((rc = s->cuda(cudaMalloc(&s->d_plan, sizeof (DevPlan) + 256),
 		    "cudaMalloc plan")))
 			break;
 		if ((rc = s->cuda(cudaMemcpy(s->d_plan, &plan->dev,

@@ -23,13 +23,16 @@ DNG_HD bool dd2(const uint8_t *p, int &v)
 	return true;
 }
 
-DNG_HD int64_t days_from_civil(int64_t y, int m, int d)
+/* days since 1970-01-01; 32-bit arithmetic (years are within +-999999), so the
+ * divisions by constants compile to multiply-shift instead of the emulated
+ * 64-bit divide */
+DNG_HD int32_t days_from_civil(int32_t y, int m, int d)
 {
 	y -= m <= 2;
-	int64_t era = (y >= 0 ? y : y - 399) / 400;
-	int64_t yoe = y - era * 400;
-	int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
-	int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+	int32_t era = (y >= 0 ? y : y - 399) / 400;
+	int32_t yoe = y - era * 400;
+	int32_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+	int32_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
 	return era * 146097 + doe - 719468;
 }
 
@@ -37,7 +40,7 @@ DNG_HD int64_t days_from_civil(int64_t y, int m, int d)
 DNG_HDN bool dng_date_parse(const uint8_t *p, int n, int64_t *ms)
 {
 	int i = 0;
-	int64_t y = 0;
+	int32_t y = 0;
 	int ysign = 0, ydig = 4;
 	if (n >= 1 && (p[0] == '+' || p[0] == '-')) {
 		ysign = p[0] == '-' ? -1 : 1;
@@ -120,8 +123,8 @@ DNG_HDN bool dng_date_parse(const uint8_t *p, int n, int64_t *ms)
 		return false;
 	if (hh == 24 && (mi || ss || msec))
 		return false;
-	int64_t t = days_from_civil(y, mo, dd) * 86400000ll +
-	    ((int64_t)(hh * 60 + mi) * 60 + ss) * 1000 + msec - off;
+	int64_t t = (int64_t)days_from_civil(y, mo, dd) * 86400000ll +
+	    (int64_t)(((hh * 60 + mi) * 60 + ss) * 1000 + msec) - off;
 	if (t > 8640000000000000ll || t < -8640000000000000ll)
 		return false;
 	*ms = t;

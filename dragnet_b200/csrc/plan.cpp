@@ -940,10 +940,10 @@ struct Compiler {
 			P.code[i] = prog[i];
 		if (ctx_cands.size() > MAX_CTX)
 			return fail(DNG_ELIMIT, "too many nested field contexts");
-		P.nctx = (u8)ctx_cands.size();
+		P.hot.nctx = (u8)ctx_cands.size();
 		int nc = 0;
 		for (size_t c = 0; c < ctx_cands.size(); c++) {
-			Ctx &x = P.ctx[c];
+			Ctx &x = P.hot.ctx[c];
 			x.parent = (int8_t)ctx_parent[c];
 			x.depth = (u8)ctx_depth[c];
 			x.cand_begin = (u16)nc;
@@ -981,9 +981,9 @@ struct Compiler {
 				if (cr.term_slot >= 0)
 					m |= 1u << cr.term_slot;
 				if (cr.child_ctx >= 0)
-					m |= P.ctx[cr.child_ctx].subtree_mask;
+					m |= P.hot.ctx[cr.child_ctx].subtree_mask;
 			}
-			P.ctx[c].subtree_mask = m;
+			P.hot.ctx[c].subtree_mask = m;
 		}
 		if (pathinfo.size() > MAX_PATHS)
 			return fail(DNG_ELIMIT, "too many distinct fields");
@@ -1002,7 +1002,7 @@ struct Compiler {
 			std::vector<std::string> keys;
 			bool arraylike = false;
 			for (size_t c = 0; c < ctx_cands.size(); c++) {
-				if (P.ctx[c].arraylike)
+				if (P.hot.ctx[c].arraylike)
 					arraylike = true;
 				for (auto &cr : ctx_cands[c])
 					if (std::find(keys.begin(), keys.end(),
@@ -1021,9 +1021,9 @@ struct Compiler {
 					kc[c][g] = cr.child_ctx;
 				}
 			}
-			FastBuilder fb(P.fast, P.trans);
+			FastBuilder fb(P.hot.fast, P.hot.trans);
 			if (arraylike || !fb.build(keys, kt, kc))
-				P.fast.ok = 0;
+				P.hot.fast.ok = 0;
 		}
 		return this->code == DNG_OK;
 	}

@@ -112,7 +112,7 @@ enum : u8 { FMT_JSON = 0, FMT_SKINNER = 1 };
  * keys, nesting > 31, a top-level scalar) ends in FS_FB and the record is
  * re-parsed by the general parser (parse_record).
  */
-enum : int { FAST_NCLS = 64, FAST_MAXSTATES = 128, FAST_MAXKEYS = 48,
+enum : int { FAST_NCLS = 64, FAST_MAXSTATES = 200, FAST_MAXKEYS = 48,
 	FAST_MAXCTX = 12 };
 enum : u8 {			/* event flags (high byte of a transition) */
 	FE_PUSH = 1, FE_POP = 2, FE_OBJ = 4, FE_KEYHIT = 8,
@@ -145,10 +145,24 @@ struct Metric {
 	u8 col0, ncols;				/* range in DevPlan::col */
 };
 
+/*
+ * The part of a plan the lock-step loop touches on every byte / event.  It is
+ * the tail of DevPlan so that CTAs can copy a plan prefix that ends with just
+ * the used rows of the transition table.
+ */
+struct alignas(16) HotPlan {
+	Ctx ctx[MAX_CTX];
+	FastTab fast;
+	u8 nctx;
+	u8 pad[7];
+	/* LAST: only the first fast.nstates rows of fast.stride entries are
+	 * meaningful and copied */
+	u16 trans[FAST_MAXSTATES * FAST_NCLS];
+};
+
 struct DevPlan {
 	Leaf code[MAX_CODE];
 	Col col[MAX_COLS];
-	Ctx ctx[MAX_CTX];
 	Cand cand[MAX_CANDS];
 	PathInfo path[MAX_PATHS];
 	Src syn[MAX_SYN];
@@ -156,23 +170,21 @@ struct DevPlan {
 	int16_t ds_entry;		/* datasource filter, -1 none */
 	u8 format;
 	u8 nmetrics;
-	u8 nctx, ncand, npaths, nslots, ncode;
+	u8 ncand, npaths, nslots, ncode;
 	int8_t root_ctx;	/* context of the record's fields object */
 	int8_t sk_fields_slot, sk_value_slot;	/* json-skinner envelope */
 	u8 pad[3];
 	char pool[POOL_BYTES];
-	FastTab fast;
-	/* LAST: only the first fast.nstates rows of fast.stride entries are
-	 * meaningful; CTAs copy just that prefix into shared memory */
-	u16 trans[FAST_MAXSTATES * FAST_NCLS];
+	HotPlan hot;		/* LAST */
 };
 
-/* bytes of a DevPlan a CTA needs in shared memory */
+/* bytes of a DevPlan a CTA copies into shared memory: everything up to and
+ * including the used rows of the transition table (which is last) */
 static inline u32 devplan_smem_bytes(const DevPlan &p)
 {
-	u32 rows = p.fast.ok ? p.fast.nstates : 0;
-	u32 n = (u32)((const char *)p.trans - (const char *)&p) +
-	    rows * p.fast.stride * 2u;
+	u32 rows = p.hot.fast.ok ? p.hot.fast.nstates : 0;
+	u32 n = (u32)((const char *)p.hot.trans - (const char *)&p) +
+	    rows * p.hot.fast.stride * 2u;
 	return (n + 127u) & ~127u;
 }
 

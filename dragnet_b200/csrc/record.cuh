@@ -228,7 +228,7 @@ DNG_HD void parse_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R)
 			pend_term = -1;
 			pend_child = -1;
 			if (depth == ctx_depth && ctx >= 0) {
-				const Ctx &cx = P.ctx[ctx];
+				const Ctx &cx = P.hot.ctx[ctx];
 				if (esc) {
 					flags |= RF_SLOW;
 					for (u32 ci = cx.cand_begin;
@@ -282,7 +282,7 @@ DNG_HD void parse_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R)
 			if ((arrbits & 1) && depth == ctx_depth && ctx >= 0) {
 				/* element of an array context: its key is the
 				 * decimal index */
-				const Ctx &cx = P.ctx[ctx];
+				const Ctx &cx = P.hot.ctx[ctx];
 				u32 lvl = cx.depth;
 				u32 idx = arr_idx[lvl]++;
 				char ib[12];
@@ -360,18 +360,18 @@ DNG_HD void parse_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R)
 				int enter = -1;
 				if (pend_child >= 0) {
 					set_mask &=
-					    ~P.ctx[pend_child].subtree_mask;
+					    ~P.hot.ctx[pend_child].subtree_mask;
 					enter = pend_child;
-				} else if (depth == 0 && P.nctx) {
+				} else if (depth == 0 && P.hot.nctx) {
 					enter = 0;
 				}
 				if (enter >= 0 && (isobj ||
-				    P.ctx[enter].arraylike)) {
+				    P.hot.ctx[enter].arraylike)) {
 					ctx = enter;
 					ctx_depth = depth + 1;
 					arrbits = (arrbits << 1) | (isobj ? 0 : 1);
 					if (!isobj)
-						arr_idx[P.ctx[enter].depth] = 0;
+						arr_idx[P.hot.ctx[enter].depth] = 0;
 				}
 				pend_term = -1;
 				pend_child = -1;
@@ -455,7 +455,7 @@ DNG_HD void parse_record(const u8 *rec, u32 len, const DevPlan &P, RecState &R)
 				set_mask |= 1u << pend_term;
 			}
 			if (pend_child >= 0)
-				set_mask &= ~P.ctx[pend_child].subtree_mask;
+				set_mask &= ~P.hot.ctx[pend_child].subtree_mask;
 			pend_term = -1;
 			pend_child = -1;
 			state = S_AFTER;
@@ -478,7 +478,7 @@ close:
 		if (((u32)(stk & 1)) != (u32)(c == '}'))
 			goto invalid;
 		if (depth == ctx_depth && ctx >= 0) {
-			const Ctx &cx = P.ctx[ctx];
+			const Ctx &cx = P.hot.ctx[ctx];
 			if (arrbits & 1) {
 				/* arr.length */
 				for (u32 ci = cx.cand_begin; ci < cx.cand_end;
@@ -542,7 +542,7 @@ DNG_HD void fast_init(FastState &s)
 }
 
 /* the value after a candidate key has ended at `end` (exclusive) */
-DNG_HD void fast_capture(FastState &s, const DevPlan &P, u64 *slots, u32 end)
+DNG_HD void fast_capture(FastState &s, const HotPlan &P, u64 *slots, u32 end)
 {
 	if (s.pend_term >= 0) {
 		slots[s.pend_term] = (u64)s.vstart | ((u64)end << 32);
@@ -557,7 +557,7 @@ DNG_HD void fast_capture(FastState &s, const DevPlan &P, u64 *slots, u32 end)
 
 /* the divergent part: runs only on bytes whose transition carries an armed
  * event flag (container open/close, a candidate key, the value after one) */
-DNG_HD void fast_event(FastState &s, const DevPlan &P, u64 *slots, u32 f,
+DNG_HD void fast_event(FastState &s, const HotPlan &P, u64 *slots, u32 f,
     u32 pos)
 {
 	const u32 VAL = FE_VALSTART | FE_VALEND_INCL | FE_VALEND_EXCL;
@@ -623,7 +623,7 @@ DNG_HD void fast_event(FastState &s, const DevPlan &P, u64 *slots, u32 f,
 		fast_capture(s, P, slots, pos + ((f & FE_VALEND_INCL) ? 1u : 0u));
 }
 
-DNG_HD void fast_step(FastState &s, const DevPlan &P, u64 *slots, u32 c, u32 pos)
+DNG_HD void fast_step(FastState &s, const HotPlan &P, u64 *slots, u32 c, u32 pos)
 {
 	u32 e = P.trans[s.state * P.fast.stride + P.fast.cls[c]];
 	s.state = e & 0xff;

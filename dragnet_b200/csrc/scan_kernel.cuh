@@ -30,7 +30,7 @@
 namespace dng {
 
 #ifndef DNG_NT
-#define DNG_NT 384			/* threads per CTA */
+#define DNG_NT 768			/* threads per CTA */
 #endif
 #ifndef DNG_TILE
 /* bytes of input a tile owns: DNG_NT slices of 13 x 16 bytes -- an odd number
@@ -41,12 +41,12 @@ namespace dng {
 #ifndef DNG_PRELAP
 #define DNG_PRELAP 4096			/* bytes staged before the tile */
 #endif
-#define DNG_CTAS_PER_SM 2
-#define DNG_NLCAP 1024			/* newline positions per pass */
-#define DNG_SSLOTS 128			/* shared hash table slots */
+#define DNG_CTAS_PER_SM 1
+#define DNG_NLCAP 2048			/* newline positions per pass */
+#define DNG_SSLOTS_MIN 64		/* shared tally slots: as many as fit (pow2) */
+#define DNG_SSLOTS_MAX 4096
 #define DNG_FASTMAX 16384		/* longest line the lock-step automaton takes */
 #define DNG_SLACK 1024			/* readable bytes past the staged window */
-#define DNG_SKEY 40			/* inline key bytes per shared slot */
 #define DNG_MAXREC (1u << 24)		/* longest line handled */
 
 enum { NCTR = 24, MCTR_PER = 8 };	/* + (MAX_METRICS-1) x MCTR_PER for fan-out */
@@ -74,12 +74,29 @@ struct GTable {
 	u32 arena_cap;
 };
 
-struct SSlot {
-	unsigned long long tag;
-	u32 count_lo, count_hi;		/* 64-bit tally as two native 32-bit atomics */
+/*
+ * Per-CTA tally cache, two tiers (hashes pick the slot, key BYTES decide):
+ *   tier 1: a few 64-byte slots with the key inline -- the common
+ *           low-cardinality case is decided entirely in shared memory;
+ *   tier 2: many 16-byte slots holding only the global entry index; a hit is
+ *           verified against the key bytes in the global arena (L2), so
+ *           hundreds to thousands of tuples still avoid global atomics.
+ * Whatever fits in neither goes to the global table directly.
+ */
+#define DNG_SKEY 40			/* inline key bytes per tier-1 slot */
+struct SSlot1 {
+	unsigned long long tag;		/* 0 empty; (hash|1) & ~READY; READY set
+					 * once klen/key are written */
+	u32 count;			/* records this launch (weights <= 255) */
 	u32 klen;
+	u32 gidx1;			/* global entry index + 1, set at flush */
 	u32 pad;
 	unsigned long long key[DNG_SKEY / 8];	/* zero padded */
+};
+struct SSlot {
+	unsigned long long tag;		/* 0 empty; (hash|1) & ~READY */
+	u32 count;
+	u32 gidx1;			/* global entry index + 1; 0 = unpublished */
 };
 
 struct ScanArgs {
@@ -92,22 +109,25 @@ struct ScanArgs {
 	u32 ntiles;
 	u32 final;			/* treat an unterminated tail as a line */
 	u32 plan_bytes;			/* devplan_smem_bytes(plan) */
+	u32 sslots;			/* tier-2 slots (power of two) */
+	u32 s1slots;			/* tier-1 slots (power of two) */
 };
 
 #define DNG_READY 0x8000000000000000ull
 
-/* the plan copy is as large as the plan needs (devplan_smem_bytes) */
-static constexpr size_t SMEM_TAB = sizeof (SSlot) * DNG_SSLOTS;
+/* the hot-plan copy is as large as the plan needs (devplan_smem_bytes) */
 static constexpr size_t SMEM_NL = sizeof (u32) * DNG_NLCAP;
 /* the slack lets lanes of a warp keep stepping (in an absorbing state) past
  * the end of their own short record while a neighbour finishes a longer one */
 static constexpr size_t SMEM_DATA = DNG_PRELAP + DNG_TILE + DNG_SLACK + 128;
-static constexpr size_t SMEM_FIXED = SMEM_TAB + SMEM_NL + SMEM_DATA;
+static constexpr size_t SMEM_FIXED = SMEM_NL + SMEM_DATA;	/* + hot plan + slots */
 
 /* ---- global table ------------------------------------------------------- */
 
-__device__ __forceinline__ void global_add(const GTable &t, u64 h,
-    const u8 *key, u32 klen, unsigned long long w)
+/* find or insert key in the global table; returns the entry index, or
+ * 0xffffffff when the table or the arena is exhausted (status is flagged) */
+__device__ __forceinline__ u32 global_find(const GTable &t, u64 h,
+    const u8 *key, u32 klen)
 {
 	unsigned long long claim = h | 1ull;
 	u32 idx = (u32)(h >> 17) & t.mask;
@@ -132,8 +152,7 @@ __device__ __forceinline__ void global_add(const GTable &t, u64 h,
 				__threadfence();
 				atomicExch(&e->koff, off + 1);
 				atomicAdd(&t.misc[1], 1u);
-				atomicAdd(&e->count, w);
-				return;
+				return idx;
 			}
 			tag = old;
 		}
@@ -147,74 +166,144 @@ __device__ __forceinline__ void global_add(const GTable &t, u64 h,
 				u32 k = 0;
 				while (k < klen && s[k] == key[k])
 					k++;
-				if (k == klen) {
-					atomicAdd(&e->count, w);
-					return;
-				}
+				if (k == klen)
+					return idx;
 			}
 		}
 		idx = (idx + 1) & t.mask;
 	}
 	atomicOr(&t.misc[2], ST_TABLE_FULL);
+	return 0xffffffffu;
 }
 
-/* ---- shared table --------------------------------------------------------- */
-
-__device__ __forceinline__ void slot_count(SSlot *s, unsigned long long w)
+__device__ __forceinline__ void global_add(const GTable &t, u64 h,
+    const u8 *key, u32 klen, unsigned long long w)
 {
-	u32 lo = (u32)w, hi = (u32)(w >> 32);
-	u32 old = atomicAdd(&s->count_lo, lo);
-	if (old + lo < old)
-		hi++;			/* carry */
-	if (hi)
-		atomicAdd(&s->count_hi, hi);
+	u32 idx = global_find(t, h, key, klen);
+	if (idx != 0xffffffffu)
+		atomicAdd(&t.entries[idx].count, w);
 }
+
+/* ---- shared tally cache ------------------------------------------------------ */
+
+/*
+ * Does global entry gi hold exactly this key?  Entries and arena bytes are
+ * written by other SMs, and L1 is not coherent, so they are read with
+ * ld.global.cg (L2); the handful of hot keys stays L2-resident.
+ */
+__device__ __forceinline__ bool entry_is(const GTable &gt, u32 gi,
+    const unsigned long long *key, u32 klen)
+{
+	const GEntry *e = &gt.entries[gi];
+	if (__ldcg(&e->klen) != klen)
+		return false;
+	const unsigned long long *s = (const unsigned long long *)
+	    (gt.arena + (__ldcg(&e->koff) - 1));	/* 8-byte aligned */
+	u32 nw = (klen + 7) >> 3;
+	for (u32 k = 0; k < nw; k++) {
+		unsigned long long a = __ldcg(&s[k]), b = key[k];
+		if (k == nw - 1 && (klen & 7)) {
+			unsigned long long m = (1ull << (8 * (klen & 7))) - 1;
+			a &= m;
+			b &= m;
+		}
+		if (a != b)
+			return false;
+	}
+	return true;
+}
+
+struct STab {
+	SSlot1 *s1;
+	SSlot *s;
+	u32 mask1, mask;		/* slots - 1 */
+};
 
 /* key: klen bytes, zero padded to a multiple of 8, 8-byte aligned */
-__device__ __forceinline__ void shared_add(SSlot *tab, const GTable &gt, u64 h,
-    const unsigned long long *key, u32 klen, unsigned long long w)
+__device__ __forceinline__ void shared_add(const STab &st, const GTable &gt,
+    u64 h, const unsigned long long *key, u32 klen, unsigned long long w)
 {
 	const u32 nw = (klen + 7) >> 3;
-	if (klen <= DNG_SKEY) {
-		unsigned long long claim = (h | 1ull) & ~DNG_READY;
-		u32 idx = (u32)(h >> 40) & (DNG_SSLOTS - 1);
-		for (u32 probe = 0; probe < 16; probe++) {
-			SSlot *s = &tab[idx];
+	if (w <= 255) {
+		const unsigned long long claim = (h | 1ull) & ~DNG_READY;
+		/* tier 1: inline keys */
+		if (klen <= DNG_SKEY) {
+			u32 idx = (u32)(h >> 40) & st.mask1;
+			for (u32 probe = 0; probe < 8; probe++) {
+				SSlot1 *s = &st.s1[idx];
+				unsigned long long tag =
+				    *(volatile unsigned long long *)&s->tag;
+				if (tag == 0) {
+					unsigned long long old =
+					    atomicCAS(&s->tag, 0ull, claim);
+					if (old == 0) {
+						s->klen = klen;
+						for (u32 k = 0; k < nw; k++)
+							s->key[k] = key[k];
+						atomicAdd(&s->count, (u32)w);
+						__threadfence_block();
+						*(volatile unsigned long long *)
+						    &s->tag = claim | DNG_READY;
+						return;
+					}
+					tag = old;
+				}
+				if ((tag & ~DNG_READY) == claim) {
+					while (!(tag & DNG_READY))
+						tag = *(volatile unsigned long
+						    long *)&s->tag;
+					__threadfence_block();
+					if (*(volatile u32 *)&s->klen == klen) {
+						const volatile unsigned long
+						    long *sk = s->key;
+						u32 k = 0;
+						while (k < nw && sk[k] == key[k])
+							k++;
+						if (k == nw) {
+							atomicAdd(&s->count,
+							    (u32)w);
+							return;
+						}
+					}
+				}
+				idx = (idx + 1) & st.mask1;
+			}
+		}
+		/* tier 2: compact slots, bytes verified in the arena */
+		u32 idx = (u32)(h >> 28) & st.mask;
+		for (u32 probe = 0; probe < 24; probe++) {
+			SSlot *s = &st.s[idx];
 			unsigned long long tag =
 			    *(volatile unsigned long long *)&s->tag;
 			if (tag == 0) {
 				unsigned long long old =
 				    atomicCAS(&s->tag, 0ull, claim);
 				if (old == 0) {
-					s->klen = klen;
-					for (u32 k = 0; k < nw; k++)
-						s->key[k] = key[k];
-					slot_count(s, w);
+					u32 gi = global_find(gt, h,
+					    (const u8 *)key, klen);
+					if (gi == 0xffffffffu) {
+						*(volatile u32 *)&s->gidx1 =
+						    0xffffffffu;
+						return;	/* status is flagged */
+					}
+					atomicAdd(&s->count, (u32)w);
 					__threadfence_block();
-					*(volatile unsigned long long *)&s->tag =
-					    claim | DNG_READY;
+					*(volatile u32 *)&s->gidx1 = gi + 1;
 					return;
 				}
 				tag = old;
 			}
-			if ((tag & ~DNG_READY) == claim) {
-				while (!(tag & DNG_READY))
-					tag = *(volatile unsigned long long *)
-					    &s->tag;
-				__threadfence_block();
-				if (*(volatile u32 *)&s->klen == klen) {
-					const volatile unsigned long long *sk =
-					    s->key;
-					u32 k = 0;
-					while (k < nw && sk[k] == key[k])
-						k++;
-					if (k == nw) {
-						slot_count(s, w);
-						return;
-					}
+			if (tag == claim) {
+				u32 g1;
+				while ((g1 = *(volatile u32 *)&s->gidx1) == 0)
+					;
+				if (g1 != 0xffffffffu &&
+				    entry_is(gt, g1 - 1, key, klen)) {
+					atomicAdd(&s->count, (u32)w);
+					return;
 				}
 			}
-			idx = (idx + 1) & (DNG_SSLOTS - 1);
+			idx = (idx + 1) & st.mask;
 		}
 	}
 	global_add(gt, h, (const u8 *)key, klen, w);
@@ -289,7 +378,7 @@ __device__ __forceinline__ u32 lds16(u32 addr)
 	u32 e_ = lds16(trb + (fs.state * stride + (cc)) * 2);		\
 	fs.state = e_ & 0xff;						\
 	if ((e_ >> 8) & fs.arm)						\
-		fast_event(fs, P, R.slots, e_ >> 8, (pos));		\
+		fast_event(fs, H, R.slots, e_ >> 8, (pos));		\
 } while (0)
 
 /* exact per-byte equality mask: 0x80 in every byte of w equal to 0x0a */
@@ -316,10 +405,10 @@ __device__ __forceinline__ u32 byte_range_mask(u32 p, u32 lo, u32 hi)
 /*
  * Fan-out (dn build / index-scan): the further metrics of an already parsed
  * and prepared record.  Out of line so that the single-metric path stays lean;
- * stage counters of metrics >= 1 go to per-CTA shared counters.
+ * stage counters of metrics >= 1 are per-thread tallies in local memory.
  */
 __device__ __noinline__ void scan_tail_fanout(const u8 *rec, const DevPlan &P,
-    RecState &R, SSlot *stab, const GTable &gt, LocalCounters &C, u32 *mctr,
+    RecState &R, STab stab, const GTable &gt, LocalCounters &C, u32 *mctr,
     u64 w)
 {
 	__align__(8) u8 kbuf[KEY_MAX + 16];
@@ -331,16 +420,17 @@ __device__ __noinline__ void scan_tail_fanout(const u8 *rec, const DevPlan &P,
 		T.synth_baddate = T.time_filtered = T.time_failedeval = 0;
 		T.aggr = T.slow = T.unsupported = 0;
 		if (process_metric(rec, P, mi, R, T, kbuf, klen))
-			shared_add(stab, gt, key_hash_words(kw, klen), kw, klen,
-			    w);
+			shared_add(stab, gt, key_hash_words(kw, klen), kw,
+			    klen, w);
+		/* per-thread tallies (local memory), reduced once per launch */
 		u32 *mc = mctr + (mi - 1) * MCTR_PER;
-		if (T.user_filtered) atomicAdd(&mc[0], 1u);
-		if (T.user_failedeval) atomicAdd(&mc[1], 1u);
-		if (T.synth_undef) atomicAdd(&mc[2], 1u);
-		if (T.synth_baddate) atomicAdd(&mc[3], 1u);
-		if (T.time_filtered) atomicAdd(&mc[4], 1u);
-		if (T.time_failedeval) atomicAdd(&mc[5], 1u);
-		if (T.aggr) atomicAdd(&mc[6], 1u);
+		mc[0] += T.user_filtered;
+		mc[1] += T.user_failedeval;
+		mc[2] += T.synth_undef;
+		mc[3] += T.synth_baddate;
+		mc[4] += T.time_filtered;
+		mc[5] += T.time_failedeval;
+		mc[6] += T.aggr;
 		C.slow += T.slow;
 		C.unsupported += T.unsupported;
 	}
@@ -348,7 +438,7 @@ __device__ __noinline__ void scan_tail_fanout(const u8 *rec, const DevPlan &P,
 
 /* stages after JSON decode + aggregation, for a parsed record */
 __device__ __forceinline__ void scan_tail(const u8 *rec, u32 len,
-    const DevPlan &P, RecState &R, SSlot *stab, const GTable &gt,
+    const DevPlan &P, RecState &R, STab stab, const GTable &gt,
     LocalCounters &C, u32 *mctr)
 {
 	(void)len;
@@ -359,14 +449,15 @@ __device__ __forceinline__ void scan_tail(const u8 *rec, u32 len,
 		return;
 	const unsigned long long *kw = (const unsigned long long *)kbuf;
 	if (process_metric(rec, P, 0, R, C, kbuf, klen))
-		shared_add(stab, gt, key_hash_words(kw, klen), kw, klen, w);
+		shared_add(stab, gt, key_hash_words(kw, klen), kw, klen,
+		    w);
 	if (P.nmetrics > 1)
 		scan_tail_fanout(rec, P, R, stab, gt, C, mctr, w);
 }
 
 /* general (branchy, exact for everything) path */
 __device__ __forceinline__ void scan_one(const u8 *rec, u32 len,
-    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C,
+    const DevPlan &P, STab stab, const GTable &gt, LocalCounters &C,
     u32 *mctr)
 {
 	RecState R;
@@ -386,7 +477,7 @@ __device__ __forceinline__ void scan_one(const u8 *rec, u32 len,
 }
 
 __device__ __noinline__ void scan_one_shared(const u8 *rec, u32 len,
-    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C,
+    const DevPlan &P, STab stab, const GTable &gt, LocalCounters &C,
     u32 *mctr)
 {
 	scan_one(rec, len, P, stab, gt, C, mctr);
@@ -395,7 +486,7 @@ __device__ __noinline__ void scan_one_shared(const u8 *rec, u32 len,
 /* out-of-line copy for lines that begin before the staged window (rare):
  * keeps the hot shared-memory instantiation of the parser small */
 __device__ __noinline__ void scan_one_global(const u8 *rec, u32 len,
-    const DevPlan &P, SSlot *stab, const GTable &gt, LocalCounters &C,
+    const DevPlan &P, STab stab, const GTable &gt, LocalCounters &C,
     u32 *mctr)
 {
 	scan_one(rec, len, P, stab, gt, C, mctr);
@@ -408,14 +499,22 @@ scan_kernel(const ScanArgs a)
 {
 	extern __shared__ __align__(128) u8 smem[];
 	DevPlan *sp = (DevPlan *)smem;
-	SSlot *stab = (SSlot *)(smem + a.plan_bytes);
-	u32 *nlpos = (u32 *)(smem + a.plan_bytes + SMEM_TAB);
-	u8 *sdata = smem + a.plan_bytes + SMEM_TAB + SMEM_NL;
+	const u32 tab1_bytes = a.s1slots * (u32)sizeof (SSlot1);
+	const u32 tab_bytes = tab1_bytes + a.sslots * (u32)sizeof (SSlot);
+	STab stab;
+	stab.s1 = (SSlot1 *)(smem + a.plan_bytes);
+	stab.s = (SSlot *)(smem + a.plan_bytes + tab1_bytes);
+	stab.mask1 = a.s1slots - 1;
+	stab.mask = a.sslots - 1;
+	u32 *nlpos = (u32 *)(smem + a.plan_bytes + tab_bytes);
+	u8 *sdata = smem + a.plan_bytes + tab_bytes + SMEM_NL;
 	__shared__ __align__(8) u64 mbar;
 	__shared__ u32 wsum[DNG_NT / 32];
 	__shared__ u32 s_total;
 	__shared__ u32 s_prev;		/* newline before the current pass */
-	__shared__ u32 s_mctr[(MAX_METRICS - 1) * MCTR_PER];
+	u32 s_mctr[(MAX_METRICS - 1) * MCTR_PER];	/* thread-local */
+	for (int k = 0; k < (MAX_METRICS - 1) * MCTR_PER; k++)
+		s_mctr[k] = 0;
 
 	const u32 tid = threadIdx.x;
 	const u32 lane = tid & 31, wid = tid >> 5;
@@ -426,16 +525,15 @@ scan_kernel(const ScanArgs a)
 		for (u32 i = tid; i < a.plan_bytes / 16; i += DNG_NT)
 			dst[i] = src[i];
 		uint4 z = make_uint4(0, 0, 0, 0);
-		uint4 *tz = (uint4 *)stab;
-		for (u32 i = tid; i < SMEM_TAB / 16; i += DNG_NT)
+		uint4 *tz = (uint4 *)stab.s1;
+		for (u32 i = tid; i < tab_bytes / 16; i += DNG_NT)
 			tz[i] = z;
 		if (tid == 0)
 			mbar_init(&mbar, 1);
-		if (tid < (MAX_METRICS - 1) * MCTR_PER)
-			s_mctr[tid] = 0;
 	}
 	__syncthreads();
-	const DevPlan &P = *sp;
+	const DevPlan &P = *sp;		/* the plan, in shared memory */
+	const HotPlan &H = P.hot;	/* the lock-step loop's tables */
 
 	LocalCounters C;
 	C.lines = C.invalid_json = C.invalid_point = 0;
@@ -601,7 +699,7 @@ scan_kernel(const ScanArgs a)
 				 * a (short, newline-terminated) record idle in the
 				 * absorbing FIN state.
 				 */
-				const bool fast = have && !islong && P.fast.ok &&
+				const bool fast = have && !islong && H.fast.ok &&
 				    len <= DNG_FASTMAX && end < wlen;
 				RecState R;
 				FastState fs;
@@ -628,9 +726,9 @@ scan_kernel(const ScanArgs a)
 					const u32 wlim = smem_u32(sdata) +
 					    DNG_PRELAP + DNG_TILE + DNG_SLACK;
 					u32 w0 = lds32(wa);
-					const u32 clsb = smem_u32(P.fast.cls);
-					const u32 trb = smem_u32(P.trans);
-					const u32 stride = P.fast.stride;
+					const u32 clsb = smem_u32(H.fast.cls);
+					const u32 trb = smem_u32(H.trans);
+					const u32 stride = H.fast.stride;
 					for (u32 i = 0; i < trip; i += 4) {
 						wa = min(wa + 4, wlim);
 						u32 w1 = lds32(wa);
@@ -682,21 +780,31 @@ scan_kernel(const ScanArgs a)
 
 	/* flush the shared table into the global one */
 	__syncthreads();
-	for (u32 i = tid; i < DNG_SSLOTS; i += DNG_NT) {
-		SSlot *s = &stab[i];
-		if (s->tag != 0) {
-			/* slots are zero-initialised and written once, so
-			 * s->key is already zero padded for key_hash() */
+	for (u32 i = tid; i < a.s1slots; i += DNG_NT) {
+		const SSlot1 *s = &stab.s1[i];
+		if (s->tag != 0 && s->count)
 			global_add(a.tab, key_hash_words(s->key, s->klen),
 			    (const u8 *)s->key, s->klen,
-			    ((unsigned long long)s->count_hi << 32) |
-			    s->count_lo);
-		}
+			    (unsigned long long)s->count);
+	}
+	for (u32 i = tid; i < a.sslots; i += DNG_NT) {
+		const SSlot *s = &stab.s[i];
+		if (s->tag != 0 && s->gidx1 != 0 && s->gidx1 != 0xffffffffu &&
+		    s->count)
+			atomicAdd(&a.tab.entries[s->gidx1 - 1].count,
+			    (unsigned long long)s->count);
 	}
 
-	if (tid < (MAX_METRICS - 1) * MCTR_PER && s_mctr[tid])
-		atomicAdd(&a.counters[NCTR + tid],
-		    (unsigned long long)s_mctr[tid]);
+	if (P.nmetrics > 1) {
+		for (u32 k = 0; k < (u32)(P.nmetrics - 1) * MCTR_PER; k++) {
+			u32 v = s_mctr[k];
+			for (int d = 16; d > 0; d >>= 1)
+				v += __shfl_xor_sync(0xffffffffu, v, d);
+			if (lane == 0 && v)
+				atomicAdd(&a.counters[NCTR + k],
+				    (unsigned long long)v);
+		}
+	}
 
 	/* counters: warp reduce, one atomic per warp per counter */
 	u32 vals[NCTR];

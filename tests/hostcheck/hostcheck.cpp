@@ -65,15 +65,15 @@ int main(int argc, char **argv)
 		const u8 *rec = (const u8 *)data.data() + pos;
 		C.lines++;
 		bool done = false;
-		if (use_fast && plan.dev.fast.ok && len <= 2048) {
+		if (use_fast && plan.dev.hot.fast.ok && len <= 2048) {
 			FastState fs;
 			fast_init(fs);
 			for (u32 i = 0; i <= len; i++)
-				fast_step(fs, plan.dev, R.slots,
+				fast_step(fs, plan.dev.hot, R.slots,
 				    i < len ? rec[i] : (u8)'\n', i);
 			/* keep stepping on garbage like neighbouring lanes do */
 			for (u32 i = 0; i < 64; i++)
-				fast_step(fs, plan.dev, R.slots,
+				fast_step(fs, plan.dev.hot, R.slots,
 				    (u8)("{\"x\":[1,\"\\\n}]"[i % 12]), len + 1 + i);
 			if (fs.state == FS_FIN) {
 				fast_finish(rec, fs, R);

@@ -16,6 +16,41 @@ rc = native.lib().dng_gen_device(ctypes.byref(params), 0, 0, n, buf.data_ptr(), 
 torch.cuda.synchronize()
 print('gen rc', rc, 'bytes', ln.value, 'sec', time.time() - t0, flush=True)
 import os
+if os.environ.get('PROBE_FANOUT'):
+    from dragnet_b200 import query as mod_query
+    mets = [{'filter': None, 'breakdowns': []},
+            {'filter': {'eq': ['req.method', 'GET']}, 'breakdowns': [
+                {'name': 'operation', 'field': 'operation'},
+                {'name': 'res.statusCode', 'field': 'res.statusCode'}]},
+            {'filter': None, 'breakdowns': [
+                {'name': 'latency', 'field': 'latency', 'aggr': 'quantize'},
+                {'name': 'host', 'field': 'host'}]},
+            {'filter': None, 'breakdowns': [
+                {'name': 'req.caller', 'field': 'req.caller'}]}]
+    if os.environ.get('PROBE_MATRIX'):
+        for interval in ('all', 'hour'):
+            for sub in ([0], [1], [2], [3], [0, 1], [0, 1, 2], [0, 1, 2, 3], [2, 2, 2, 2], [0, 0, 0, 0]):
+                qs = [mod_query.metricQuery(mets[i], None, None, interval, 'time') for i in sub]
+                multi = mod_query.scan_plan_multi(qs, time_field='time')
+                for rep in range(3):
+                    r = datasource_gpu.run_plan(multi, device_buffers=[(buf.data_ptr(), ln.value)])
+                print('interval=%-4s metrics=%-14s kernel %.2f ms points %d' % (interval, sub, r.stats['kernel_ms'], len(r.points)), flush=True)
+        sys.exit(0)
+    qs = [mod_query.metricQuery(m, None, None, os.environ.get('PROBE_INTERVAL', 'hour'), 'time') for m in mets]
+    multi = mod_query.scan_plan_multi(qs, time_field='time')
+    for rep in range(int(os.environ.get('PROBE_REPS', 3))):
+        r = datasource_gpu.run_plan(multi, device_buffers=[(buf.data_ptr(), ln.value)])
+    ms = r.stats['kernel_ms']
+    if os.environ.get('PROBE_FANOUT') == 'only':
+        sys.exit(0)
+    print('fanout4 (one pass, 4 metrics, hourly __dn_ts): kernel %.2f ms  %.1f Mrec/s  points %d' % (ms, n / ms / 1e3, len(r.points)), flush=True)
+    tot = 0
+    for q in qs:
+        plan = mod_query.scan_plan(q, time_field='time')
+        for rep in range(3):
+            r = datasource_gpu.run_plan(plan, device_buffers=[(buf.data_ptr(), ln.value)])
+        tot += r.stats['kernel_ms']
+    print('same 4 metrics as 4 separate scans: kernel %.2f ms total' % tot, flush=True)
 for name in os.environ.get('PROBE_Q', 'count,C2,C3,C4,C5,date').split(','):
     argv, ds = corpus.BASELINE_QUERIES[name]
     plan = corpus.make_plan(argv, ds)
