@@ -302,6 +302,10 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 			 * when two CTAs share an SM (1 KB is reserved per CTA) */
 			size_t per_cta = prop.sharedMemPerMultiprocessor /
 			    DNG_CTAS_PER_SM - 1024 - 256;
+			/* a single block may not exceed the opt-in limit, which
+			 * also covers the kernel's static shared variables */
+			per_cta = std::min(per_cta,
+			    (size_t)prop.sharedMemPerBlockOptin - 1024 - 512);
 			size_t used = SMEM_FIXED + s->plan_bytes;
 			size_t room = per_cta > used ? per_cta - used : 0;
 			/* tier 1: 128 inline-key slots (64 when tight); tier 2:
@@ -324,7 +328,11 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		    s->s1slots * sizeof (SSlot1) >
 		    prop.sharedMemPerBlockOptin - 1024) {
 			rc = s->fail(DNG_ELIMIT, "plan does not fit in shared "
-			    "memory");
+			    "memory (fixed " + std::to_string(SMEM_FIXED) +
+			    " + plan " + std::to_string(s->plan_bytes) +
+			    " + tier2 " + std::to_string(s->sslots) + " + tier1 " +
+			    std::to_string(s->s1slots) + " slots > " +
+			    std::to_string(prop.sharedMemPerBlockOptin) + ")");
 			break;
 		}
 		if ((rc = s->cuda(cudaStreamCreateWithFlags(&s->stream,
