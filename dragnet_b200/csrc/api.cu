@@ -86,6 +86,10 @@ struct dng_scan {
 	double kernel_ms = 0;
 	uint64_t launches = 0, kernel_bytes = 0, bytes_fed = 0;
 	bool finished = false;
+	/* record templates (tmpl.h), learned from the head of the input */
+	bool tmpl_enabled = true, tmpl_tried = false;
+	u8 *d_tmpl = nullptr;
+	u32 tmpl_bytes = 0, ntemplates = 0;
 	std::string err;
 	int err_code = 0;
 
@@ -120,12 +124,114 @@ cudaEvent_t get_event(dng_scan *s)
 	return e;
 }
 
+/* shared memory set aside for the template trie when sizing the tally cache */
+static constexpr size_t TMPL_RESERVE = 4096;
+
+/* the record parser's view of one sample line per template candidate */
+__global__ void resolve_pairs_kernel(const DevPlan *plan, const u8 *lines,
+    const u32 *se, u32 n, TResolved *out)
+{
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	RecState R;
+	parse_record(lines + se[2 * i], se[2 * i + 1] - se[2 * i], *plan, R);
+	out[i].flags = R.flags;
+	out[i].set_mask = R.set_mask;
+	for (int k = 0; k < MAX_SLOTS; k++)
+		out[i].slots[k] = ((R.set_mask >> k) & 1) ? R.slots[k] : 0;
+}
+
+/*
+ * Learn record templates from the head of the first data this scan sees
+ * (device memory): skeletons on the host (lexical only), what their
+ * wildcards mean to the plan from the device's own parser.  Failure to learn
+ * anything is not an error: the kernel then parses every record itself.
+ */
+int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
+    unsigned long long nbytes)
+{
+	s->tmpl_tried = true;
+	if (!s->tmpl_enabled)
+		return 0;
+	size_t n = (size_t)std::min<unsigned long long>(nbytes - start,
+	    TMPL_SAMPLE_BYTES);
+	std::vector<u8> head(n);
+	CK(s, cudaMemcpyAsync(head.data(), data + start, n,
+	    cudaMemcpyDeviceToHost, s->stream));
+	CK(s, cudaStreamSynchronize(s->stream));
+	std::vector<TCandidate> cands;
+	tmpl_candidates(head.data(), n, TMPL_MAX_LEAVES, cands);
+	if (cands.empty())
+		return 0;
+	std::vector<u8> lines;
+	std::vector<u32> offs(1, 0);
+	for (const TCandidate &c : cands) {
+		lines.insert(lines.end(), c.sample.begin(), c.sample.end());
+		lines.push_back('\n');
+		offs.push_back((u32)lines.size());
+	}
+	u8 *d_lines = nullptr;
+	u32 *d_offs = nullptr;
+	TResolved *d_res = nullptr;
+	std::vector<TResolved> res(cands.size());
+	cudaError_t e = cudaMalloc(&d_lines, lines.size() + 16);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&d_offs, 2 * offs.size() * sizeof (u32));
+	if (e == cudaSuccess)
+		e = cudaMalloc(&d_res, res.size() * sizeof (TResolved));
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(d_lines, lines.data(), lines.size(),
+		    cudaMemcpyHostToDevice, s->stream);
+	/* line i = [offs[i], offs[i + 1] - 1): keep starts and ends apart */
+	std::vector<u32> se;
+	for (size_t i = 0; i < cands.size(); i++) {
+		se.push_back(offs[i]);
+		se.push_back(offs[i + 1] - 1);
+	}
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(d_offs, se.data(), se.size() * sizeof (u32),
+		    cudaMemcpyHostToDevice, s->stream);
+	if (e == cudaSuccess) {
+		resolve_pairs_kernel<<<1, 32, 0, s->stream>>>(s->d_plan, d_lines,
+		    d_offs, (u32)cands.size(), d_res);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(res.data(), d_res,
+		    res.size() * sizeof (TResolved), cudaMemcpyDeviceToHost,
+		    s->stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(s->stream);
+	cudaFree(d_lines);
+	cudaFree(d_offs);
+	cudaFree(d_res);
+	if (e != cudaSuccess)
+		return s->cuda(e, "template resolve");
+	std::vector<u8> blob;
+	u32 nt = 0;
+	tmpl_build(cands, res, TMPL_RESERVE, blob, &nt);
+	if (blob.empty())
+		return 0;
+	size_t padded = (blob.size() + 127) & ~(size_t)127;
+	blob.resize(padded, 0);
+	CK(s, cudaMalloc(&s->d_tmpl, padded));
+	CK(s, cudaMemcpyAsync(s->d_tmpl, blob.data(), padded,
+	    cudaMemcpyHostToDevice, s->stream));
+	CK(s, cudaStreamSynchronize(s->stream));
+	s->tmpl_bytes = (u32)padded;
+	s->ntemplates = nt;
+	return 0;
+}
+
 /* launch the scan kernel over data[start, nbytes) */
 int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
     unsigned long long nbytes, bool final)
 {
 	if (nbytes <= start)
 		return 0;
+	if (!s->tmpl_tried && learn_templates(s, data, start, nbytes))
+		return s->err_code;
 	ScanArgs a;
 	a.data = data;
 	a.start = start;
@@ -138,10 +244,12 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 	a.plan_bytes = s->plan_bytes;
 	a.sslots = s->sslots;
 	a.s1slots = s->s1slots;
+	a.tmpl = s->d_tmpl;
+	a.tmpl_bytes = s->tmpl_bytes;
 	u32 grid = std::min<u32>(a.ntiles, (u32)s->sm_count * DNG_CTAS_PER_SM);
 	cudaEvent_t e0 = get_event(s), e1 = get_event(s);
 	cudaEventRecord(e0, s->stream);
-	scan_kernel<<<grid, DNG_NT, SMEM_FIXED + s->plan_bytes +
+	scan_kernel<<<grid, DNG_NT, SMEM_FIXED + s->plan_bytes + s->tmpl_bytes +
 	    s->sslots * sizeof (SSlot) + s->s1slots * sizeof (SSlot1),
 	    s->stream>>>(a);
 	cudaEventRecord(e1, s->stream);
@@ -296,6 +404,8 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		    "cudaGetDeviceProperties")))
 			break;
 		s->sm_count = prop.multiProcessorCount;
+		if (const char *ev = getenv("DNG_TEMPLATES"))
+			s->tmpl_enabled = atoi(ev) != 0;
 		s->plan_bytes = devplan_smem_bytes(plan->dev);
 		{
 			/* the tally cache takes whatever shared memory is left
@@ -306,7 +416,7 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 			 * also covers the kernel's static shared variables */
 			per_cta = std::min(per_cta,
 			    (size_t)prop.sharedMemPerBlockOptin - 1024 - 512);
-			size_t used = SMEM_FIXED + s->plan_bytes;
+			size_t used = SMEM_FIXED + s->plan_bytes + TMPL_RESERVE;
 			size_t room = per_cta > used ? per_cta - used : 0;
 			/* tier 1: 128 inline-key slots (64 when tight); tier 2:
 			 * as many compact slots as still fit (power of two) */
@@ -324,8 +434,8 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		    (int)prop.sharedMemPerBlockOptin - 1024),
 		    "cudaFuncSetAttribute")))
 			break;
-		if (SMEM_FIXED + s->plan_bytes + s->sslots * sizeof (SSlot) +
-		    s->s1slots * sizeof (SSlot1) >
+		if (SMEM_FIXED + s->plan_bytes + TMPL_RESERVE +
+		    s->sslots * sizeof (SSlot) + s->s1slots * sizeof (SSlot1) >
 		    prop.sharedMemPerBlockOptin - 1024) {
 			rc = s->fail(DNG_ELIMIT, "plan does not fit in shared "
 			    "memory (fixed " + std::to_string(SMEM_FIXED) +
@@ -896,6 +1006,35 @@ const char *dng_scan_error(const dng_scan *s)
 	return s ? s->err.c_str() : "null scan";
 }
 
+int dng_scan_set_templates(dng_scan *s, int enable)
+{
+	if (!s)
+		return DNG_EINVAL;
+	if (s->tmpl_tried)
+		return s->fail(DNG_EINVAL, "templates are fixed once data has "
+		    "been fed");
+	s->tmpl_enabled = enable != 0;
+	return DNG_OK;
+}
+
+int dng_scan_template_stats(dng_scan *s, uint64_t *templates,
+    uint64_t *templated_records)
+{
+	if (!s)
+		return DNG_EINVAL;
+	cudaSetDevice(s->device);
+	if (dng_scan_sync(s))
+		return s->err_code;
+	unsigned long long c = 0;
+	CK(s, cudaMemcpy(&c, s->d_counters + CTR_TMPL, sizeof (c),
+	    cudaMemcpyDeviceToHost));
+	if (templates)
+		*templates = s->ntemplates;
+	if (templated_records)
+		*templated_records = c;
+	return DNG_OK;
+}
+
 int dng_scan_kernel_stats(dng_scan *s, double *kernel_ms, uint64_t *launches,
     uint64_t *kernel_bytes)
 {
@@ -937,6 +1076,7 @@ void dng_scan_destroy(dng_scan *s)
 			cudaEventDestroy(s->file_done[i]);
 	}
 	cudaFree(s->d_plan);
+	cudaFree(s->d_tmpl);
 	cudaFree(s->tab.entries);
 	cudaFree(s->tab.arena);
 	cudaFree(s->tab.misc);

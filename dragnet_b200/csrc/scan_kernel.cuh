@@ -26,6 +26,7 @@
 
 #include <cuda_runtime.h>
 #include "record.cuh"
+#include "tmpl.cuh"
 
 namespace dng {
 
@@ -54,7 +55,7 @@ enum {
 	CTR_LINES = 0, CTR_INVALID_JSON, CTR_INVALID_POINT,
 	CTR_DS_FILTERED, CTR_DS_FAILED, CTR_USER_FILTERED, CTR_USER_FAILED,
 	CTR_SYNTH_UNDEF, CTR_SYNTH_BADDATE, CTR_TIME_FILTERED, CTR_TIME_FAILED,
-	CTR_AGGR, CTR_SLOW, CTR_UNSUPPORTED, CTR_LONG
+	CTR_AGGR, CTR_SLOW, CTR_UNSUPPORTED, CTR_LONG, CTR_TMPL
 };
 
 enum { ST_TABLE_FULL = 1, ST_ARENA_FULL = 2 };
@@ -111,6 +112,8 @@ struct ScanArgs {
 	u32 plan_bytes;			/* devplan_smem_bytes(plan) */
 	u32 sslots;			/* tier-2 slots (power of two) */
 	u32 s1slots;			/* tier-1 slots (power of two) */
+	const u8 *tmpl;			/* record templates (tmpl.h blob) or null */
+	u32 tmpl_bytes;			/* multiple of 128, 0 = no templates */
 };
 
 #define DNG_READY 0x8000000000000000ull
@@ -120,7 +123,9 @@ static constexpr size_t SMEM_NL = sizeof (u32) * DNG_NLCAP;
 /* the slack lets lanes of a warp keep stepping (in an absorbing state) past
  * the end of their own short record while a neighbour finishes a longer one */
 static constexpr size_t SMEM_DATA = DNG_PRELAP + DNG_TILE + DNG_SLACK + 128;
-static constexpr size_t SMEM_FIXED = SMEM_NL + SMEM_DATA;	/* + hot plan + slots */
+/* records the templates did not take, per pass (u16 indexes) */
+static constexpr size_t SMEM_FQ = sizeof (u16) * DNG_NLCAP;
+static constexpr size_t SMEM_FIXED = SMEM_NL + SMEM_FQ + SMEM_DATA;	/* + hot plan + slots */
 
 /* ---- global table ------------------------------------------------------- */
 
@@ -373,6 +378,68 @@ __device__ __forceinline__ u32 lds16(u32 addr)
 	return v;
 }
 
+__device__ __forceinline__ uint4 lds128(u32 addr)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+	    : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
+
+/*
+ * Shared-memory access for tmpl_match(): the record in the staged tile (any
+ * byte alignment: aligned 32-bit loads + a funnel shift) and the trie blob.
+ */
+struct TmplSmem {
+	u32 ra;			/* record start */
+	u32 nodes, leaves, pool;
+
+	struct Cur {
+		u32 wa, w0, sh;
+		__device__ __forceinline__ u32 next()
+		{
+			wa += 4;
+			const u32 w1 = lds32(wa);
+			const u32 d = __funnelshift_r(w0, w1, sh);
+			w0 = w1;
+			return d;
+		}
+	};
+	__device__ __forceinline__ Cur cursor(u32 off) const
+	{
+		Cur c;
+		const u32 a = ra + off;
+		c.sh = (a & 3) * 8;
+		c.wa = a & ~3u;
+		c.w0 = lds32(c.wa);
+		return c;
+	}
+	__device__ __forceinline__ u32 byte(u32 off) const
+	{
+		return lds8(ra + off);
+	}
+	__device__ __forceinline__ u32 word(u32 off) const
+	{
+		Cur c = cursor(off);
+		return c.next();
+	}
+	__device__ __forceinline__ TQuad node(u32 i) const
+	{
+		const uint4 v = lds128(nodes + i * 16);
+		TQuad q;
+		q.x = v.x; q.y = v.y; q.z = v.z; q.w = v.w;
+		return q;
+	}
+	__device__ __forceinline__ u32 lit(u32 off) const
+	{
+		return lds32(pool + off);
+	}
+	__device__ __forceinline__ u32 leaf(u32 i) const
+	{
+		return lds32(leaves + 4 * i);
+	}
+};
+
 /* one automaton step on a class code (see record.cuh fast_step) */
 #define FAST_STEP(cc, pos) do {						\
 	u32 e_ = lds16(trb + (fs.state * stride + (cc)) * 2);		\
@@ -502,16 +569,19 @@ scan_kernel(const ScanArgs a)
 	const u32 tab1_bytes = a.s1slots * (u32)sizeof (SSlot1);
 	const u32 tab_bytes = tab1_bytes + a.sslots * (u32)sizeof (SSlot);
 	STab stab;
-	stab.s1 = (SSlot1 *)(smem + a.plan_bytes);
-	stab.s = (SSlot *)(smem + a.plan_bytes + tab1_bytes);
+	const u32 fixed_bytes = a.plan_bytes + a.tmpl_bytes;
+	stab.s1 = (SSlot1 *)(smem + fixed_bytes);
+	stab.s = (SSlot *)(smem + fixed_bytes + tab1_bytes);
 	stab.mask1 = a.s1slots - 1;
 	stab.mask = a.sslots - 1;
-	u32 *nlpos = (u32 *)(smem + a.plan_bytes + tab_bytes);
-	u8 *sdata = smem + a.plan_bytes + tab_bytes + SMEM_NL;
+	u32 *nlpos = (u32 *)(smem + fixed_bytes + tab_bytes);
+	u16 *failq = (u16 *)(smem + fixed_bytes + tab_bytes + SMEM_NL);
+	u8 *sdata = smem + fixed_bytes + tab_bytes + SMEM_NL + SMEM_FQ;
 	__shared__ __align__(8) u64 mbar;
 	__shared__ u32 wsum[DNG_NT / 32];
 	__shared__ u32 s_total;
 	__shared__ u32 s_prev;		/* newline before the current pass */
+	__shared__ u32 s_nfail;		/* records the templates did not take */
 	u32 s_mctr[(MAX_METRICS - 1) * MCTR_PER];	/* thread-local */
 	for (int k = 0; k < (MAX_METRICS - 1) * MCTR_PER; k++)
 		s_mctr[k] = 0;
@@ -524,6 +594,10 @@ scan_kernel(const ScanArgs a)
 		uint4 *dst = (uint4 *)sp;
 		for (u32 i = tid; i < a.plan_bytes / 16; i += DNG_NT)
 			dst[i] = src[i];
+		const uint4 *tsrc = (const uint4 *)a.tmpl;
+		uint4 *tdst = (uint4 *)(smem + a.plan_bytes);
+		for (u32 i = tid; i < a.tmpl_bytes / 16; i += DNG_NT)
+			tdst[i] = tsrc[i];
 		uint4 z = make_uint4(0, 0, 0, 0);
 		uint4 *tz = (uint4 *)stab.s1;
 		for (u32 i = tid; i < tab_bytes / 16; i += DNG_NT)
@@ -534,6 +608,19 @@ scan_kernel(const ScanArgs a)
 	__syncthreads();
 	const DevPlan &P = *sp;		/* the plan, in shared memory */
 	const HotPlan &H = P.hot;	/* the lock-step loop's tables */
+
+	/* record templates, if the host learned any for this input */
+	const bool use_tmpl = a.tmpl_bytes != 0;
+	TmplSmem tm;
+	tm.ra = 0;
+	tm.nodes = smem_u32(smem + a.plan_bytes) + (u32)sizeof (THdr);
+	tm.leaves = tm.pool = 0;
+	if (use_tmpl) {
+		const THdr *th = (const THdr *)(smem + a.plan_bytes);
+		tm.leaves = smem_u32(smem + a.plan_bytes) + th->leaf_off;
+		tm.pool = smem_u32(smem + a.plan_bytes) + th->pool_off;
+	}
+	u32 ntmpl = 0;
 
 	LocalCounters C;
 	C.lines = C.invalid_json = C.invalid_point = 0;
@@ -668,9 +755,23 @@ scan_kernel(const ScanArgs a)
 			u32 n = total - pass;
 			if (n > DNG_NLCAP)
 				n = DNG_NLCAP;
-			for (u32 rb = 0; rb < n; rb += DNG_NT) {
-				const u32 r = rb + tid;
-				const bool have = r < n;
+			if (tid == 0)
+				s_nfail = 0;
+			__syncthreads();
+			/*
+			 * Phase 0 (only with templates): every record is tried
+			 * against the template trie; what does not match is
+			 * queued.  Phase 1: the queued records (or, without
+			 * templates, all records) go through the byte automaton
+			 * and its fallbacks, densely packed into warps again.
+			 */
+			for (u32 phase = use_tmpl ? 0 : 1; phase < 2; phase++) {
+			const u32 nn = (phase == 1 && use_tmpl) ? s_nfail : n;
+			for (u32 rb = 0; rb < nn; rb += DNG_NT) {
+				const bool have = rb + tid < nn;
+				u32 r = rb + tid;
+				if (have && phase == 1 && use_tmpl)
+					r = failq[r];
 				u32 end = 0, beg = 0;
 				bool islong = false;
 				if (have) {
@@ -693,6 +794,23 @@ scan_kernel(const ScanArgs a)
 					}
 				}
 				const u32 len = end - beg;
+				RecState R;
+				bool parsed = false;
+				const u8 *rec = sdata;
+				if (phase == 0) {
+					/* newline-terminated lines inside the window */
+					const bool elig = have && !islong && end < wlen &&
+					    len <= TMPL_MAX_LINE;
+					rec = sdata + beg;
+					tm.ra = smem_u32(rec);
+					parsed = tmpl_match(tm, len, R, elig);
+					if (parsed) {
+						C.lines++;
+						ntmpl++;
+					} else if (have) {
+						failq[atomicAdd(&s_nfail, 1u)] = (u16)r;
+					}
+				} else {
 				/*
 				 * Lock-step fast path: every lane steps the plan's
 				 * byte automaton over its own record; lanes without
@@ -701,12 +819,11 @@ scan_kernel(const ScanArgs a)
 				 */
 				const bool fast = have && !islong && H.fast.ok &&
 				    len <= DNG_FASTMAX && end < wlen;
-				RecState R;
 				FastState fs;
 				fast_init(fs);
 				if (!fast)
 					fs.state = FS_FIN;
-				const u8 *rec = sdata + (fast ? beg : 0);
+				rec = sdata + (fast ? beg : 0);
 				u32 trip = __reduce_max_sync(0xffffffffu,
 				    fast ? len + 1 : 0);
 				/*
@@ -747,8 +864,7 @@ scan_kernel(const ScanArgs a)
 				if (fast && fs.state == FS_FIN) {
 					C.lines++;
 					fast_finish(rec, fs, R);
-					scan_tail(rec, len, P, R, stab, a.tab, C,
-					    s_mctr);
+					parsed = true;
 				} else if (fast && fs.state == FS_ERR) {
 					C.lines++;
 					C.invalid_json++;
@@ -769,6 +885,12 @@ scan_kernel(const ScanArgs a)
 					    DNG_MAXREC, ws + end - q), P, stab,
 					    a.tab, C, s_mctr);
 				}
+				}
+				if (parsed)
+					scan_tail(rec, len, P, R, stab, a.tab, C,
+					    s_mctr);
+			}
+			__syncthreads();
 			}
 			__syncthreads();
 			if (tid == 0)
@@ -825,8 +947,9 @@ scan_kernel(const ScanArgs a)
 	vals[CTR_SLOW] = C.slow;
 	vals[CTR_UNSUPPORTED] = C.unsupported;
 	vals[CTR_LONG] = nlong;
+	vals[CTR_TMPL] = ntmpl;
 #pragma unroll
-	for (int k = 0; k <= CTR_LONG; k++) {
+	for (int k = 0; k <= CTR_TMPL; k++) {
 		u32 v = vals[k];
 		for (int d = 16; d > 0; d >>= 1)
 			v += __shfl_xor_sync(0xffffffffu, v, d);

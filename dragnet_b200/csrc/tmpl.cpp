@@ -1,0 +1,440 @@
+/*
+ * tmpl.cpp: host side of record templates (tmpl.h): lexical skeletons of a
+ * sample of the input, and the trie blob the kernel matches against.  Nothing
+ * here parses records for their values: what a template's wildcards mean to
+ * the plan is resolved by running the device's own record parser on one sample
+ * line per template (api.cu resolve_kernel).
+ */
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+
+#include "tmpl.h"
+
+namespace dng {
+
+static inline bool is_ws(u8 c)
+{
+	return c == ' ' || c == '\t' || c == '\r' || c == '\n';
+}
+
+bool tmpl_skeletonize(const u8 *s, u32 n, std::vector<TSeg> &out)
+{
+	out.clear();
+	std::string stack;		/* '{' or '[' per open container */
+	bool expect_key = false;
+	u32 i = 0, lit_start = 0;
+	while (i < n) {
+		u8 c = s[i];
+		if (c == '"') {
+			u32 j = i + 1;
+			while (j < n && s[j] != '"') {
+				if (s[j] == '\\')
+					j++;
+				j++;
+			}
+			if (j >= n)
+				return false;
+			if (!stack.empty() && stack.back() == '{' && expect_key) {
+				expect_key = false;
+				i = j + 1;
+				continue;
+			}
+			TSeg g;
+			g.lit.assign((const char *)s + lit_start, i + 1 - lit_start);
+			g.kind = TK_STR;
+			g.woff = i + 1;
+			g.wlen = j - (i + 1);
+			out.push_back(g);
+			lit_start = j;
+			i = j + 1;
+		} else if (c == '{' || c == '[') {
+			if (stack.size() >= 64)
+				return false;
+			stack.push_back((char)c);
+			expect_key = c == '{';
+			i++;
+		} else if (c == '}' || c == ']') {
+			if (stack.empty() || stack.back() != (c == '}' ? '{' : '['))
+				return false;
+			stack.pop_back();
+			expect_key = false;
+			i++;
+		} else if (c == ',') {
+			expect_key = !stack.empty() && stack.back() == '{';
+			i++;
+		} else if (c == ':' || is_ws(c)) {
+			i++;
+		} else {
+			u32 j = i;
+			while (j < n && s[j] != ',' && s[j] != ']' && s[j] != '}' &&
+			    s[j] != ':' && s[j] != '"' && !is_ws(s[j]))
+				j++;
+			TSeg g;
+			g.lit.assign((const char *)s + lit_start, i - lit_start);
+			g.kind = TK_BARE;
+			g.woff = i;
+			g.wlen = j - i;
+			out.push_back(g);
+			lit_start = j;
+			i = j;
+		}
+	}
+	if (!stack.empty())
+		return false;
+	TSeg g;
+	g.lit.assign((const char *)s + lit_start, n - lit_start);
+	g.kind = TK_NONE;
+	g.woff = n;
+	g.wlen = 0;
+	out.push_back(g);
+	return true;
+}
+
+void tmpl_candidates(const u8 *data, size_t len, size_t maxk,
+    std::vector<TCandidate> &out)
+{
+	out.clear();
+	std::map<std::string, size_t> seen;
+	std::vector<TSeg> segs;
+	size_t pos = 0, nlines = 0;
+	while (pos < len && nlines < 8192) {
+		const u8 *nl = (const u8 *)memchr(data + pos, '\n', len - pos);
+		if (!nl)
+			break;
+		size_t n = (size_t)(nl - (data + pos));
+		const u8 *line = data + pos;
+		pos += n + 1;
+		nlines++;
+		if (n == 0 || n > TMPL_MAX_LINE)
+			continue;
+		if (!tmpl_skeletonize(line, (u32)n, segs))
+			continue;
+		std::string key;
+		for (const TSeg &g : segs) {
+			key += g.lit;
+			key.push_back((char)(1 + g.kind));
+		}
+		auto it = seen.find(key);
+		if (it != seen.end()) {
+			out[it->second].count++;
+			continue;
+		}
+		if (seen.size() >= 256)
+			continue;
+		seen[key] = out.size();
+		TCandidate c;
+		c.sample.assign((const char *)line, n);
+		c.segs = segs;
+		c.count = 1;
+		out.push_back(c);
+	}
+	std::stable_sort(out.begin(), out.end(),
+	    [](const TCandidate &a, const TCandidate &b) {
+		    return a.count > b.count;
+	    });
+	/* shapes seen in under 0.5% of the lines are not worth a trie branch */
+	size_t keep = 0;
+	while (keep < out.size() && keep < maxk &&
+	    (size_t)out[keep].count * 200 >= nlines)
+		keep++;
+	out.resize(keep);
+}
+
+namespace {
+
+struct PSeg {			/* a template segment with its captures */
+	std::string lit;
+	u8 kind, cap, poscap;
+};
+
+struct PTmpl {
+	std::vector<PSeg> segs;
+	u32 set_mask;
+	int want[MAX_SLOTS];	/* segment that must supply each set slot */
+};
+
+/* attach the parser's slot values to the candidate's wildcards */
+bool plan_template(const TCandidate &c, const TResolved &r, PTmpl &t)
+{
+	if (r.flags != 0)
+		return false;
+	t.segs.clear();
+	std::vector<u32> start;		/* offset of each literal in the sample */
+	u32 pos = 0;
+	for (const TSeg &g : c.segs) {
+		PSeg p;
+		p.lit = g.lit;
+		p.kind = g.kind;
+		p.cap = p.poscap = 0;
+		t.segs.push_back(p);
+		start.push_back(pos);
+		pos = g.woff + g.wlen;
+	}
+	t.set_mask = r.set_mask;
+	for (int s = 0; s < MAX_SLOTS; s++)
+		t.want[s] = -1;
+	/* first cut the literals so that every captured container opens one */
+	for (u32 s = 0; s < MAX_SLOTS; s++) {
+		if (!((r.set_mask >> s) & 1))
+			continue;
+		u64 v = r.slots[s];
+		u32 type = (u32)(v >> 56) & 0xf, off = (u32)v;
+		if (type != T_OBJ && type != T_ARR)
+			continue;
+		for (size_t i = 0; i < t.segs.size(); i++) {
+			if (off <= start[i] || off >= start[i] + t.segs[i].lit.size())
+				continue;
+			u32 d = off - start[i];
+			PSeg head;
+			head.lit = t.segs[i].lit.substr(0, d);
+			head.kind = TK_NONE;
+			head.cap = head.poscap = 0;
+			t.segs[i].lit.erase(0, d);
+			t.segs.insert(t.segs.begin() + i, head);
+			start.insert(start.begin() + i + 1, off);
+			break;
+		}
+	}
+	for (u32 s = 0; s < MAX_SLOTS; s++) {
+		if (!((r.set_mask >> s) & 1))
+			continue;
+		u64 v = r.slots[s];
+		u32 type = (u32)(v >> 56) & 0xf, flags = (u32)(v >> 60) & 0xf;
+		u32 off = (u32)v;
+		if (flags & VF_INLINE)
+			return false;
+		bool found = false;
+		for (size_t i = 0; i < t.segs.size() && !found; i++) {
+			PSeg &g = t.segs[i];
+			if (type == T_OBJ || type == T_ARR) {
+				if (start[i] != off || g.lit.empty() ||
+				    g.lit[0] != (type == T_OBJ ? '{' : '['))
+					continue;
+				if (g.poscap)
+					return false;
+				g.poscap = (u8)(s + 1);
+			} else {
+				if (g.kind != (type == T_STR ? TK_STR : TK_BARE) ||
+				    start[i] + g.lit.size() != off)
+					continue;
+				if (g.cap)
+					return false;
+				g.cap = (u8)(s + 1);
+			}
+			t.want[s] = (int)i;
+			found = true;
+		}
+		if (!found)
+			return false;
+	}
+	return true;
+}
+
+struct BNode {
+	std::string lit;
+	u8 kind, cap, poscap;
+	std::vector<int> kids;
+	int leaf;
+};
+
+struct Trie {
+	std::vector<BNode> nodes;	/* nodes[0] = virtual root */
+	std::vector<u32> leaf_mask;
+	size_t pool;
+
+	Trie() : pool(0) {
+		BNode r;
+		r.kind = r.cap = r.poscap = 0;
+		r.leaf = -1;
+		nodes.push_back(r);
+	}
+
+	bool insert(const PTmpl &t) {
+		int cur = 0;
+		for (size_t i = 0; i < t.segs.size(); i++) {
+			const PSeg &g = t.segs[i];
+			int hit = -1;
+			for (int k : nodes[cur].kids)
+				if (nodes[k].lit == g.lit && nodes[k].kind == g.kind)
+					hit = k;
+			if (hit < 0) {
+				BNode b;
+				b.lit = g.lit;
+				b.kind = g.kind;
+				b.cap = g.cap;
+				b.poscap = g.poscap;
+				b.leaf = -1;
+				hit = (int)nodes.size();
+				nodes.push_back(b);
+				nodes[cur].kids.push_back(hit);
+				pool += (g.lit.size() + 3) / 4 * 4 + 4;
+			} else {
+				BNode &b = nodes[hit];
+				if (g.cap) {
+					if (b.cap && b.cap != g.cap)
+						return false;
+					b.cap = g.cap;
+				}
+				if (g.poscap) {
+					if (b.poscap && b.poscap != g.poscap)
+						return false;
+					b.poscap = g.poscap;
+				}
+			}
+			cur = hit;
+		}
+		if (nodes[cur].leaf >= 0 || !nodes[cur].kids.empty())
+			return false;
+		nodes[cur].leaf = (int)leaf_mask.size();
+		leaf_mask.push_back(t.set_mask);
+		/* an interior node may not also end another template */
+		for (const BNode &b : nodes)
+			if (b.leaf >= 0 && !b.kids.empty())
+				return false;
+		return true;
+	}
+
+	/* does matching t's own shape leave every set slot filled from the
+	 * segment the parser took it from? */
+	bool verify(const PTmpl &t) const {
+		int last[MAX_SLOTS];
+		for (int s = 0; s < MAX_SLOTS; s++)
+			last[s] = -1;
+		int cur = 0;
+		for (size_t i = 0; i < t.segs.size(); i++) {
+			const PSeg &g = t.segs[i];
+			int hit = -1;
+			for (int k : nodes[cur].kids) {
+				if (nodes[k].lit == g.lit && nodes[k].kind == g.kind) {
+					hit = k;
+					break;
+				}
+				/* an earlier wildcard-less sibling whose literal
+				 * is a prefix of ours would be taken instead
+				 * (the matcher does not backtrack) */
+				if (nodes[k].kind == TK_NONE &&
+				    nodes[k].lit.size() <= g.lit.size() &&
+				    g.lit.compare(0, nodes[k].lit.size(),
+				    nodes[k].lit) == 0)
+					return false;
+			}
+			if (hit < 0)
+				return false;
+			const BNode &b = nodes[hit];
+			if (b.poscap)
+				last[b.poscap - 1] = (int)i;
+			if (b.cap)
+				last[b.cap - 1] = (int)i;
+			cur = hit;
+		}
+		if (nodes[cur].leaf < 0 ||
+		    leaf_mask[nodes[cur].leaf] != t.set_mask)
+			return false;
+		for (int s = 0; s < MAX_SLOTS; s++)
+			if (((t.set_mask >> s) & 1) && last[s] != t.want[s])
+				return false;
+		return true;
+	}
+};
+
+size_t blob_bytes(const Trie &tr)
+{
+	size_t nn = tr.nodes.size() - 1;
+	size_t n = sizeof (THdr) + nn * sizeof (TNode) + 4 * tr.leaf_mask.size();
+	n = (n + 15) & ~(size_t)15;
+	return ((n + tr.pool + 15) & ~(size_t)15);
+}
+
+bool build_trie(const std::vector<PTmpl> &ts, Trie &tr, size_t max_bytes)
+{
+	for (const PTmpl &t : ts)
+		if (!tr.insert(t))
+			return false;
+	for (const PTmpl &t : ts)
+		if (!tr.verify(t))
+			return false;
+	return tr.nodes.size() - 1 <= TMPL_MAX_NODES &&
+	    tr.pool <= TMPL_MAX_POOL && tr.leaf_mask.size() <= TMPL_MAX_LEAVES &&
+	    blob_bytes(tr) <= max_bytes;
+}
+
+} /* namespace */
+
+void tmpl_build(const std::vector<TCandidate> &cands,
+    const std::vector<TResolved> &res, size_t max_bytes, std::vector<u8> &blob,
+    u32 *ntemplates)
+{
+	blob.clear();
+	if (ntemplates)
+		*ntemplates = 0;
+	std::vector<PTmpl> acc;
+	for (size_t i = 0; i < cands.size() && i < res.size(); i++) {
+		PTmpl t;
+		if (!plan_template(cands[i], res[i], t))
+			continue;
+		acc.push_back(t);
+		Trie probe;
+		if (!build_trie(acc, probe, max_bytes))
+			acc.pop_back();
+	}
+	if (acc.empty())
+		return;
+	Trie tr;
+	if (!build_trie(acc, tr, max_bytes))
+		return;
+	if (ntemplates)
+		*ntemplates = (u32)acc.size();
+
+	/* number the nodes: the children of one node are consecutive and
+	 * chained through `alt`; the root's first child is node 0 */
+	size_t nn = tr.nodes.size() - 1;
+	std::vector<int> index(tr.nodes.size(), -1);
+	std::vector<int> order;
+	std::vector<int> queue(1, 0);
+	for (size_t q = 0; q < queue.size(); q++) {
+		for (int k : tr.nodes[queue[q]].kids) {
+			index[k] = (int)order.size();
+			order.push_back(k);
+			queue.push_back(k);
+		}
+	}
+	std::vector<TNode> out(nn);
+	std::string pool;
+	for (size_t q = 0; q < queue.size(); q++) {
+		const std::vector<int> &kids = tr.nodes[queue[q]].kids;
+		for (size_t j = 0; j < kids.size(); j++) {
+			const BNode &b = tr.nodes[kids[j]];
+			TNode &o = out[index[kids[j]]];
+			memset(&o, 0, sizeof (o));
+			o.lit = (u16)pool.size();
+			o.len = (u16)b.lit.size();
+			pool += b.lit;
+			pool.append((4 - pool.size() % 4) % 4 + 4, '\0');
+			u32 rem = (u32)b.lit.size() % 4;
+			o.lastmask = rem ? (1u << (8 * rem)) - 1 : 0xffffffffu;
+			o.kind = b.kind;
+			o.cap = b.cap;
+			o.poscap = b.poscap;
+			o.alt = j + 1 < kids.size() ? (u16)index[kids[j + 1]] :
+			    (u16)TN_NOALT;
+			o.next = b.leaf >= 0 ? (u16)(TN_LEAF | b.leaf) :
+			    (u16)index[b.kids[0]];
+		}
+	}
+	THdr h;
+	memset(&h, 0, sizeof (h));
+	h.nnodes = (u16)nn;
+	h.nleaves = (u16)tr.leaf_mask.size();
+	h.leaf_off = (u32)(sizeof (THdr) + nn * sizeof (TNode));
+	h.pool_off = (h.leaf_off + 4 * h.nleaves + 15) & ~15u;
+	h.bytes = (u32)((h.pool_off + pool.size() + 15) & ~(size_t)15);
+	blob.assign(h.bytes, 0);
+	memcpy(blob.data(), &h, sizeof (h));
+	memcpy(blob.data() + sizeof (THdr), out.data(), nn * sizeof (TNode));
+	memcpy(blob.data() + h.leaf_off, tr.leaf_mask.data(), 4 * h.nleaves);
+	memcpy(blob.data() + h.pool_off, pool.data(), pool.size());
+}
+
+} /* namespace dng */

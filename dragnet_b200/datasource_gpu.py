@@ -77,13 +77,16 @@ def stage_counters(plan, c, npoints):
     return out
 
 
-def run_plan(plan, files=(), chunks=None, device=0, device_buffers=None):
+def run_plan(plan, files=(), chunks=None, device=0, device_buffers=None,
+             templates=None):
     """Drive one scan through the C ABI.  Input is any of: files (read by the
     library), host byte chunks, or (ptr, len) device buffers."""
     import json
     p = native.Plan(json.dumps(plan, separators=(',', ':')))
     s = native.Scan(p, device)
     try:
+        if templates is not None:
+            s.set_templates(templates)
         for f in files:
             s.feed_file(f)
         for c in (chunks or ()):
@@ -93,6 +96,7 @@ def run_plan(plan, files=(), chunks=None, device=0, device_buffers=None):
         res = s.finish()
         flat = s.counters()
         stats = s.kernel_stats()
+        stats.update(s.template_stats())
         pts = []
         if 'metrics' in plan:
             # fan-out: points are tagged like the reference tags them

@@ -70,6 +70,9 @@ _SIGS = [
     ('dng_scan_kernel_stats', ctypes.c_int,
      [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64),
       ctypes.POINTER(ctypes.c_uint64)]),
+    ('dng_scan_set_templates', ctypes.c_int, [_P, ctypes.c_int]),
+    ('dng_scan_template_stats', ctypes.c_int,
+     [_P, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     ('dng_pinned_alloc', _P, [ctypes.c_size_t]),
     ('dng_pinned_free', None, [_P]),
     ('dng_result_count', ctypes.c_size_t, [_P]),
@@ -329,6 +332,18 @@ class Scan(object):
                self.handle)
         return {'kernel_ms': ms.value, 'launches': int(n.value),
                 'kernel_bytes': int(b.value)}
+
+    def set_templates(self, enable):
+        """Record templates on/off (default on); before the first feed."""
+        _check(lib().dng_scan_set_templates(self.handle, 1 if enable else 0),
+               self.handle)
+
+    def template_stats(self):
+        t = ctypes.c_uint64()
+        r = ctypes.c_uint64()
+        _check(lib().dng_scan_template_stats(self.handle, ctypes.byref(t),
+                                             ctypes.byref(r)), self.handle)
+        return {'templates': int(t.value), 'templated_records': int(r.value)}
 
     def close(self):
         if self.handle:

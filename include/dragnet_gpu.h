@@ -142,6 +142,18 @@ void dng_scan_destroy(dng_scan *scan);
 int dng_scan_kernel_stats(dng_scan *scan, double *kernel_ms,
     uint64_t *launches, uint64_t *kernel_bytes);
 
+/*
+ * Record templates: the scan learns the few shapes (key order + punctuation)
+ * the input's records repeat from the head of the first data it is fed, and
+ * matches records against them before falling back to its byte automaton;
+ * results never depend on it.  On by default (environment DNG_TEMPLATES=0
+ * turns it off); set_templates must precede the first feed.  The stats give
+ * the number of templates in use and how many records they accepted.
+ */
+int dng_scan_set_templates(dng_scan *scan, int enable);
+int dng_scan_template_stats(dng_scan *scan, uint64_t *templates,
+    uint64_t *templated_records);
+
 void *dng_pinned_alloc(size_t len);
 void dng_pinned_free(void *p);
 

@@ -218,3 +218,31 @@ BASELINE_QUERIES = {
     'lq': (['-b', 'dataLatency[aggr=lquantize,step=100],host'], None),
     'url': (['-b', 'req.url'], None),
 }
+
+
+# scalar forms behind one skeleton ({"a":<bare>,"s":"<string>"}): what the
+# template matcher's wildcard scans must accept, reject or hand to the automaton
+BARE_FORMS = [b'0', b'-0', b'1', b'12', b'123', b'1234', b'12345', b'123456',
+              b'1234567', b'12345678', b'123456789', b'123456789012345',
+              b'1234567890123456', b'12345678901234567890', b'-1', b'-12',
+              b'-123', b'-1234', b'-12345', b'-123456789012345',
+              b'-1234567890123456', b'0.5', b'-0.5', b'1e5', b'1E+5', b'1e-5',
+              b'1.5e3', b'1.0', b'100.000', b'0e0', b'0.0', b'-0.0', b'1e400',
+              b'-1e400', b'1e-400', b'01', b'-01', b'00', b'1.', b'.5', b'1e',
+              b'1e+', b'-', b'+1', b'0x10', b'1a', b'1 ', b' 1', b'true',
+              b'false', b'null', b'tru', b'nul', b'falsy', b'truee', b'nulll',
+              b'True', b'NaN', b'Infinity', b'-Infinity', b'1,', b'1}',
+              b'"x"', b'{}', b'[]', b'[1]', b'{"b":1}', b'']
+STR_FORMS = [b'', b'a', b'ab', b'abc', b'abcd', b'abcde', b'abcdefgh',
+             b'abcdefghi', b'x' * 63, b'x' * 64, b'x' * 65, b'\\n', b'a\\"b',
+             b'\\\\', b'a\\u0041', b'\x01', b'a\tb', b'\x7f', b'\xc3\xa9',
+             b'\xf0\x9f\x98\x80', b'\xff\xfe', b'a"', b'"', b'a\\']
+
+
+def scalar_lines():
+    out = []
+    for i, f in enumerate(BARE_FORMS):
+        out.append(b'{"a":' + f + b',"s":"k%d"}' % (i % 5))
+    for i, f in enumerate(STR_FORMS):
+        out.append(b'{"a":%d,"s":"' % (i % 7) + f + b'"}')
+    return out

@@ -9,6 +9,7 @@
  */
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -17,6 +18,7 @@
 #include <vector>
 
 #include "../../dragnet_b200/csrc/record.cuh"
+#include "../../dragnet_b200/csrc/tmpl.cuh"
 #include "../../dragnet_b200/csrc/result.h"
 #include "../../include/dragnet_gpu.h"
 
@@ -51,7 +53,32 @@ int main(int argc, char **argv)
 	LocalCounters C;
 	memset(&C, 0, sizeof (C));
 	bool use_fast = getenv("DNG_HOSTCHECK_FAST") != nullptr;
-	unsigned long nfast = 0;
+	unsigned long nfast = 0, ntmpl = 0;
+	/* DNG_HOSTCHECK_TMPL: learn record templates from the head of the input
+	 * (as api.cu does, with the parser run on the host instead of by
+	 * resolve_kernel) and try them before the other parsers */
+	std::vector<u8> blob;
+	if (getenv("DNG_HOSTCHECK_TMPL") != nullptr) {
+		std::vector<TCandidate> cands;
+		tmpl_candidates((const u8 *)data.data(),
+		    std::min<size_t>(data.size(), TMPL_SAMPLE_BYTES),
+		    TMPL_MAX_LEAVES, cands);
+		std::vector<TResolved> res(cands.size());
+		for (size_t i = 0; i < cands.size(); i++) {
+			static RecState TR;
+			parse_record((const u8 *)cands[i].sample.data(),
+			    (u32)cands[i].sample.size(), plan.dev, TR);
+			res[i].flags = TR.flags;
+			res[i].set_mask = TR.set_mask;
+			memcpy(res[i].slots, TR.slots, sizeof (TR.slots));
+		}
+		tmpl_build(cands, res, 1 << 20, blob, nullptr);
+		if (getenv("DNG_HOSTCHECK_TMPL_DEBUG"))
+			fprintf(stderr, "tmpl: %zu candidates, blob %zu bytes, "
+			    "%u nodes, %u leaves\n", cands.size(), blob.size(),
+			    blob.empty() ? 0 : ((THdr *)blob.data())->nnodes,
+			    blob.empty() ? 0 : ((THdr *)blob.data())->nleaves);
+	}
 	static LocalCounters MCs[MAX_METRICS];
 	memset(MCs, 0, sizeof (MCs));
 	std::map<std::string, uint64_t> table;
@@ -65,7 +92,17 @@ int main(int argc, char **argv)
 		const u8 *rec = (const u8 *)data.data() + pos;
 		C.lines++;
 		bool done = false;
-		if (use_fast && plan.dev.hot.fast.ok && len <= 2048) {
+		if (!blob.empty() && nl != std::string::npos) {
+			TmplHostMem m;
+			m.rec = rec;
+			m.len = len;
+			m.blob = blob.data();
+			if (tmpl_match(m, len, R, true)) {
+				done = true;
+				ntmpl++;
+			}
+		}
+		if (!done && use_fast && plan.dev.hot.fast.ok && len <= 2048) {
 			FastState fs;
 			fast_init(fs);
 			for (u32 i = 0; i <= len; i++)
@@ -154,6 +191,6 @@ int main(int argc, char **argv)
 		    M.time_failedeval, M.aggr);
 		C.unsupported += M.unsupported;
 	}
-	printf("],\"nfast\":%lu}\n", nfast);
+	printf("],\"nfast\":%lu,\"ntmpl\":%lu}\n", nfast, ntmpl);
 	return 0;
 }

@@ -197,3 +197,82 @@ def test_long_lines_and_large_counts(tmp_path):
     act_p, act_c = gpu_engine(plan, [path])
     assert canon_points(act_p) == canon_points(exp_p)
     assert act_c == exp_c
+
+
+def test_record_templates_do_not_change_results():
+    """Record templates (tmpl.h): on mktestdata-shaped input nearly every
+    record is taken by a learned template; the points and every counter must
+    equal the run with templates switched off."""
+    from dragnet_b200 import datasource_gpu, native
+    n = 300000
+    data = native.gen_host(native.gen_params(total_records=n), 0, n)
+    for name in sorted(corpus.BASELINE_QUERIES):
+        argv, ds = corpus.BASELINE_QUERIES[name]
+        plan = corpus.make_plan(argv, ds)
+        on = datasource_gpu.run_plan(plan, chunks=[data], templates=True)
+        off = datasource_gpu.run_plan(plan, chunks=[data], templates=False)
+        assert canon_points(on.points) == canon_points(off.points), name
+        assert on.flat_counters == off.flat_counters, name
+        assert off.stats['templated_records'] == 0
+        assert on.stats['templates'] >= 3, on.stats
+        assert on.stats['templated_records'] >= 0.99 * n, on.stats
+
+
+@pytest.mark.parametrize('rot', [0, 24, 48, 72, 96, 120, 144])
+def test_edge_lines_with_templates_learned_from_different_heads(rot, tmp_path):
+    """Templates are learned from the first lines of the input: rotate the
+    edge corpus so that every odd shape gets to be a template once."""
+    lines = corpus.EDGE_LINES[rot:] + corpus.EDGE_LINES[:rot]
+    path = _write(tmp_path, 'edge.log', lines)
+    for argv, ds in corpus.EDGE_QUERIES[::4]:
+        plan = corpus.make_plan(argv, ds)
+        exp_p, exp_c = py_engine(plan, [path])
+        act_p, act_c = gpu_engine(plan, [path])
+        assert canon_points(act_p) == canon_points(exp_p), (rot, argv)
+        assert act_c == exp_c, (rot, argv)
+
+
+def test_templates_with_unmatched_records_in_the_same_tile(tmp_path):
+    """Templated records interleaved with records of other shapes, invalid
+    lines, escapes in captured strings and non-integer numbers: the matcher
+    must hand exactly those to the automaton."""
+    from dragnet_b200 import native
+    n = 60000
+    data = native.gen_host(native.gen_params(total_records=n), 0, n)
+    recs = data.split(b'\n')[:-1]
+    odd = [b'{"req":{"method":"PATCH"},"latency":3}',
+           b'{"time":"x","req":{"method":"G\\u0045T"},"latency":1.5e1}',
+           b'{"req":{"method":"GET"}', b'', b'[1,2]',
+           recs[5].replace(b'"GET"', b'"G\\tT"').replace(b'"PUT"', b'"P\\\\T"'),
+           recs[6].replace(b'"latency":', b'"latency":-0.0e+0,"latency":'),
+           recs[7].replace(b'}}', b'} }'), recs[8] + b' ', recs[9][:-1]]
+    out = []
+    for i, r in enumerate(recs):
+        out.append(r)
+        if i % 97 == 0:
+            out.append(odd[(i // 97) % len(odd)])
+    path = _write(tmp_path, 'mixed.log', out)
+    for argv in (['-b', 'req.method'], ['-b', 'latency[aggr=quantize]'],
+                 ['-b', 'req.method,latency', '-f',
+                  '{"ne":["req.method","HEAD"]}']):
+        plan = corpus.make_plan(argv)
+        exp_p, exp_c = py_engine(plan, [path])
+        act_p, act_c = gpu_engine(plan, [path])
+        assert canon_points(act_p) == canon_points(exp_p), argv
+        assert act_c == exp_c, argv
+
+
+def test_scalar_forms_behind_one_template(tmp_path):
+    """Every number / literal / string-body form in one record shape, so that
+    the template's wildcard scans see them all (see tests/corpus.py)."""
+    from dragnet_b200 import datasource_gpu
+    lines = [b'{"a":7,"s":"k0"}'] * 3 + corpus.scalar_lines()
+    path = _write(tmp_path, 'scalars.log', lines)
+    for argv in (['-b', 'a'], ['-b', 's'], ['-b', 'a[aggr=quantize]'],
+                 ['-b', 'a,s', '-f', '{"ge":["a",1]}']):
+        plan = corpus.make_plan(argv)
+        exp_p, exp_c = py_engine(plan, [path])
+        r = datasource_gpu.run_plan(plan, files=[path])
+        assert canon_points(r.points) == canon_points(exp_p), argv
+        assert r.counters == exp_c, argv
+        assert r.stats['templated_records'] > 20, r.stats

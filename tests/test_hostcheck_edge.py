@@ -8,14 +8,17 @@ import sys
 import pytest
 
 
-@pytest.fixture(params=['general', 'fast'], autouse=True)
+@pytest.fixture(params=['general', 'fast', 'tmpl'], autouse=True)
 def parser_mode(request, monkeypatch):
-    """Run every case with the general parser only, and with the lock-step
-    fast automaton (+ fallback) the kernel uses."""
-    if request.param == 'fast':
+    """Run every case with the general parser only, with the lock-step fast
+    automaton (+ fallback), and with record templates learned from the input
+    in front of both -- the three tiers the kernel uses."""
+    monkeypatch.delenv('DNG_HOSTCHECK_FAST', raising=False)
+    monkeypatch.delenv('DNG_HOSTCHECK_TMPL', raising=False)
+    if request.param in ('fast', 'tmpl'):
         monkeypatch.setenv('DNG_HOSTCHECK_FAST', '1')
-    else:
-        monkeypatch.delenv('DNG_HOSTCHECK_FAST', raising=False)
+    if request.param == 'tmpl':
+        monkeypatch.setenv('DNG_HOSTCHECK_TMPL', '1')
 
 sys.path.insert(0, os.path.dirname(__file__))
 import corpus  # noqa: E402
@@ -54,3 +57,24 @@ def test_random_lines(seed, tmp_path):
     path = _write(tmp_path, 'rand.log', corpus.random_lines(seed, 400))
     for argv, ds in corpus.EDGE_QUERIES[:24:3]:
         _compare(corpus.make_plan(argv, ds), path)
+
+
+@pytest.mark.parametrize('rot', [24, 48, 72, 96, 120, 144])
+def test_edge_lines_rotated(rot, tmp_path):
+    """Templates are learned from the head of the input: rotate the corpus so
+    that every odd shape gets to be a template once."""
+    lines = corpus.EDGE_LINES[rot:] + corpus.EDGE_LINES[:rot]
+    path = _write(tmp_path, 'edge.log', lines)
+    for argv, ds in corpus.EDGE_QUERIES[::3]:
+        _compare(corpus.make_plan(argv, ds), path)
+
+
+def test_scalar_forms_behind_one_template(tmp_path):
+    """Every number / literal / string-body form in the same record shape: in
+    template mode the first lines make the template and all others meet its
+    wildcard scans."""
+    lines = [b'{"a":7,"s":"k0"}'] * 3 + corpus.scalar_lines()
+    path = _write(tmp_path, 'scalars.log', lines)
+    for argv in (['-b', 'a'], ['-b', 's'], ['-b', 'a[aggr=quantize]'],
+                 ['-b', 'a,s', '-f', '{"ge":["a",1]}']):
+        _compare(corpus.make_plan(argv), path)

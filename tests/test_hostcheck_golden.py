@@ -9,14 +9,17 @@ import sys
 import pytest
 
 
-@pytest.fixture(params=['general', 'fast'], autouse=True)
+@pytest.fixture(params=['general', 'fast', 'tmpl'], autouse=True)
 def parser_mode(request, monkeypatch):
-    """Run every case with the general parser only, and with the lock-step
-    fast automaton (+ fallback) the kernel uses."""
-    if request.param == 'fast':
+    """Run every case with the general parser only, with the lock-step fast
+    automaton (+ fallback), and with record templates learned from the input
+    in front of both -- the three tiers the kernel uses."""
+    monkeypatch.delenv('DNG_HOSTCHECK_FAST', raising=False)
+    monkeypatch.delenv('DNG_HOSTCHECK_TMPL', raising=False)
+    if request.param in ('fast', 'tmpl'):
         monkeypatch.setenv('DNG_HOSTCHECK_FAST', '1')
-    else:
-        monkeypatch.delenv('DNG_HOSTCHECK_FAST', raising=False)
+    if request.param == 'tmpl':
+        monkeypatch.setenv('DNG_HOSTCHECK_TMPL', '1')
 
 sys.path.insert(0, os.path.dirname(__file__))
 from engines import hostcheck_engine  # noqa: E402

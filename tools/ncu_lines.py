@@ -36,7 +36,9 @@ for cub in glob.glob(os.path.join(d, 'api*.cubin')):
         m = re.match(r'^\s*/\*([0-9a-f]{4,})\*/\s+(\S.*?);', l)
         if m and fn and 'scan_kernel' in fn and 'ScanArgs' in fn:
             addr2line[int(m.group(1), 16)] = (fl, ln)
-raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'],
+skip = os.environ.get('NCU_SKIP', '0')
+raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv',
+                      '--launch-skip', skip, '--launch-count', '1'],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 h = next(i for i, r in enumerate(rows[:5]) if 'Instructions Executed' in r)
@@ -46,7 +48,8 @@ ci, cs, ca = hdr.index('Instructions Executed'), hdr.index('# Samples'), \
 cw, cwi = hdr.index('L1 Wavefronts Shared'), \
     hdr.index('L1 Wavefronts Shared Ideal')
 base = None
-agg = collections.defaultdict(lambda: [0, 0, 0, 0])
+ct = hdr.index('Thread Instructions Executed')
+agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0])
 tot = tots = 0
 for r in rows[h + 1:]:
     try:
@@ -61,10 +64,20 @@ for r in rows[h + 1:]:
     v[1] += float(r[cs] or 0)
     v[2] += float(r[cw] or 0)
     v[3] += float(r[cwi] or 0)
+    v[4] += float(r[ct] or 0)
     tot += float(r[ci] or 0)
     tots += float(r[cs] or 0)
 print('total warp-instructions %.0f, samples %.0f' % (tot, tots))
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-    print('%-22s:%4d  inst %5.1f%%  samples %5.1f%%  smem wavefronts %10d '
-          '(ideal %9d)' % (k[0], k[1], 100 * v[0] / tot, 100 * v[1] / tots,
-                           v[2], v[3]))
+byfile = collections.defaultdict(lambda: [0, 0])
+for k, v in agg.items():
+    byfile[k[0]][0] += v[0]
+    byfile[k[0]][1] += v[1]
+for f, v in sorted(byfile.items(), key=lambda kv: -kv[1][1]):
+    print('  %-22s inst %5.1f%%  samples %5.1f%%' % (f, 100 * v[0] / tot, 100 * v[1] / tots))
+key = (lambda kv: -kv[1][0]) if os.environ.get('NCU_BY') == 'inst' else \
+    (lambda kv: -kv[1][1])
+for k, v in sorted(agg.items(), key=key)[:top]:
+    print('%-22s:%4d  inst %5.1f%%  thr/inst %4.1f  samples %5.1f%%  smem '
+          'wavefronts %10d (ideal %9d)' % (k[0], k[1], 100 * v[0] / tot,
+                                           v[4] / max(v[0], 1),
+                                           100 * v[1] / tots, v[2], v[3]))

@@ -54,8 +54,12 @@ if os.environ.get('PROBE_FANOUT'):
 for name in os.environ.get('PROBE_Q', 'count,C2,C3,C4,C5,date').split(','):
     argv, ds = corpus.BASELINE_QUERIES[name]
     plan = corpus.make_plan(argv, ds)
-    for rep in range(3):
-        r = datasource_gpu.run_plan(plan, device_buffers=[(buf.data_ptr(), ln.value)])
-    ms = r.stats['kernel_ms']
-    print('%-6s kernel %.2f ms  %.1f Mrec/s  %.1f GB/s  points %d  lines %d slow %d' % (
-        name, ms, n / ms / 1e3, ln.value / ms / 1e6, len(r.points), r.flat_counters['lines'], r.flat_counters['slowpath_records']), flush=True)
+    for tm in (True, False):
+        for rep in range(3):
+            t1 = time.time()
+            r = datasource_gpu.run_plan(plan, device_buffers=[(buf.data_ptr(), ln.value)], templates=tm)
+            wall = (time.time() - t1) * 1e3
+        ms = r.stats['kernel_ms']
+        print('%-6s templates=%d kernel %.2f ms  %.1f Mrec/s  %.1f GB/s  wall %.2f ms  points %d  lines %d slow %d  tmpl %d/%d' % (
+            name, tm, ms, n / ms / 1e3, ln.value / ms / 1e6, wall, len(r.points), r.flat_counters['lines'], r.flat_counters['slowpath_records'],
+            r.stats['templates'], r.stats['templated_records']), flush=True)
