@@ -88,6 +88,10 @@ struct dng_scan {
 	bool finished = false;
 	/* record templates (tmpl.h), learned from the head of the input */
 	bool tmpl_enabled = true, tmpl_tried = false;
+	/* kernel geometry: per-warp chunks for short lines, CTA tiles otherwise */
+	bool warp_kernel = false;
+	int kernel_pref = 0;		/* DNG_KERNEL: 0 auto, 1 tile, 2 warp */
+	u32 w_sslots = 0, w_s1slots = 0;
 	u8 *d_tmpl = nullptr;
 	u32 tmpl_bytes = 0, ntemplates = 0;
 	std::string err;
@@ -152,7 +156,7 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
     unsigned long long nbytes)
 {
 	s->tmpl_tried = true;
-	if (!s->tmpl_enabled)
+	if (!s->tmpl_enabled && s->kernel_pref != 0)
 		return 0;
 	size_t n = (size_t)std::min<unsigned long long>(nbytes - start,
 	    TMPL_SAMPLE_BYTES);
@@ -160,6 +164,23 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 	CK(s, cudaMemcpyAsync(head.data(), data + start, n,
 	    cudaMemcpyDeviceToHost, s->stream));
 	CK(s, cudaStreamSynchronize(s->stream));
+	if (s->kernel_pref == 0) {
+		/* short lines: every warp stages its own chunk (scan_kernel_w);
+		 * otherwise CTA-wide tiles, whose window holds long lines */
+		size_t longest = 0, run = 0;
+		for (size_t i = 0; i < n; i++) {
+			if (head[i] == '\n') {
+				longest = std::max(longest, run);
+				run = 0;
+			} else {
+				run++;
+			}
+		}
+		longest = std::max(longest, run);
+		s->warp_kernel = longest <= DNG_W_MAXLINE;
+	}
+	if (!s->tmpl_enabled)
+		return 0;
 	std::vector<TCandidate> cands;
 	tmpl_candidates(head.data(), n, TMPL_MAX_LEAVES, cands);
 	if (cands.empty())
@@ -239,19 +260,32 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 	a.plan = s->d_plan;
 	a.counters = s->d_counters;
 	a.tab = s->tab;
-	a.ntiles = (u32)((nbytes + DNG_TILE - 1) / DNG_TILE);
 	a.final = final ? 1 : 0;
 	a.plan_bytes = s->plan_bytes;
-	a.sslots = s->sslots;
-	a.s1slots = s->s1slots;
 	a.tmpl = s->d_tmpl;
 	a.tmpl_bytes = s->tmpl_bytes;
-	u32 grid = std::min<u32>(a.ntiles, (u32)s->sm_count * DNG_CTAS_PER_SM);
 	cudaEvent_t e0 = get_event(s), e1 = get_event(s);
-	cudaEventRecord(e0, s->stream);
-	scan_kernel<<<grid, DNG_NT, SMEM_FIXED + s->plan_bytes + s->tmpl_bytes +
-	    s->sslots * sizeof (SSlot) + s->s1slots * sizeof (SSlot1),
-	    s->stream>>>(a);
+	if (s->warp_kernel) {
+		a.ntiles = (u32)((nbytes + DNG_W_CHUNK - 1) / DNG_W_CHUNK);
+		a.sslots = s->w_sslots;
+		a.s1slots = s->w_s1slots;
+		u32 grid = std::min<u32>((a.ntiles + DNG_NW - 1) / DNG_NW,
+		    (u32)s->sm_count);
+		cudaEventRecord(e0, s->stream);
+		scan_kernel_w<<<grid, DNG_NT, SMEM_W_FIXED + s->plan_bytes +
+		    s->tmpl_bytes + a.sslots * sizeof (SSlot) +
+		    a.s1slots * sizeof (SSlot1), s->stream>>>(a);
+	} else {
+		a.ntiles = (u32)((nbytes + DNG_TILE - 1) / DNG_TILE);
+		a.sslots = s->sslots;
+		a.s1slots = s->s1slots;
+		u32 grid = std::min<u32>(a.ntiles,
+		    (u32)s->sm_count * DNG_CTAS_PER_SM);
+		cudaEventRecord(e0, s->stream);
+		scan_kernel<<<grid, DNG_NT, SMEM_FIXED + s->plan_bytes +
+		    s->tmpl_bytes + a.sslots * sizeof (SSlot) +
+		    a.s1slots * sizeof (SSlot1), s->stream>>>(a);
+	}
 	cudaEventRecord(e1, s->stream);
 	s->ev_pairs.emplace_back(e0, e1);
 	s->launches++;
@@ -428,8 +462,31 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 			    (size_t)n * 2 * sizeof (SSlot) <= left)
 				n *= 2;
 			s->sslots = n;
+			/* the per-warp kernel's fixed part differs: size its
+			 * tally cache separately */
+			size_t usedw = SMEM_W_FIXED + s->plan_bytes + TMPL_RESERVE;
+			size_t roomw = per_cta > usedw ? per_cta - usedw : 0;
+			s->w_s1slots = roomw >= 24576 ? 256 : roomw >= 12288 ? 128 : 64;
+			size_t t1w = (size_t)s->w_s1slots * sizeof (SSlot1);
+			size_t leftw = roomw > t1w ? roomw - t1w : 0;
+			u32 nw = DNG_SSLOTS_MIN;
+			while (nw * 2 <= DNG_SSLOTS_MAX &&
+			    (size_t)nw * 2 * sizeof (SSlot) <= leftw)
+				nw *= 2;
+			s->w_sslots = nw;
+		}
+		if (const char *ev = getenv("DNG_KERNEL")) {
+			/* tuning/testing: force one kernel geometry */
+			s->kernel_pref = !strcmp(ev, "tile") ? 1 :
+			    !strcmp(ev, "warp") ? 2 : 0;
+			s->warp_kernel = s->kernel_pref == 2;
 		}
 		if ((rc = s->cuda(cudaFuncSetAttribute(scan_kernel,
+		    cudaFuncAttributeMaxDynamicSharedMemorySize,
+		    (int)prop.sharedMemPerBlockOptin - 1024),
+		    "cudaFuncSetAttribute")))
+			break;
+		if ((rc = s->cuda(cudaFuncSetAttribute(scan_kernel_w,
 		    cudaFuncAttributeMaxDynamicSharedMemorySize,
 		    (int)prop.sharedMemPerBlockOptin - 1024),
 		    "cudaFuncSetAttribute")))
@@ -444,6 +501,14 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 			    std::to_string(s->s1slots) + " slots > " +
 			    std::to_string(prop.sharedMemPerBlockOptin) + ")");
 			break;
+		}
+		if (SMEM_W_FIXED + s->plan_bytes + TMPL_RESERVE +
+		    s->w_sslots * sizeof (SSlot) +
+		    s->w_s1slots * sizeof (SSlot1) >
+		    prop.sharedMemPerBlockOptin - 1024) {
+			/* no room for the per-warp geometry with this plan */
+			s->kernel_pref = 1;
+			s->warp_kernel = false;
 		}
 		if ((rc = s->cuda(cudaStreamCreateWithFlags(&s->stream,
 		    cudaStreamNonBlocking), "cudaStreamCreate")))
@@ -957,6 +1022,18 @@ int dng_scan_finish(dng_scan *s, dng_result **out)
 	if (misc[2] & ST_ARENA_FULL)
 		return s->fail(DNG_ELIMIT, "group-key arena exhausted (raise "
 		    "DNG_ARENA_BYTES)");
+#ifdef DNG_PROFILE_PHASES
+	{	/* tuning builds only: where a tile's cycles go (see scan_kernel) */
+		unsigned long long pc[NCTR];
+		CK(s, cudaMemcpy(pc, s->d_counters, sizeof (pc),
+		    cudaMemcpyDeviceToHost));
+		double nw = (double)pc[18] ? (double)pc[18] : 1;
+		fprintf(stderr, "phases: per warp-tile cycles: load-wait %.0f "
+		    "index %.0f records-busy %.0f records-phase %.0f total %.0f "
+		    "(%llu warp-tiles)\n", pc[19] / nw, pc[20] / nw, pc[16] / nw,
+		    pc[17] / nw, pc[21] / nw, pc[18]);
+	}
+#endif
 	dng_counters c;
 	if (dng_scan_counters(s, &c))
 		return s->err_code;

@@ -42,8 +42,12 @@ namespace dng {
 #ifndef DNG_PRELAP
 #define DNG_PRELAP 4096			/* bytes staged before the tile */
 #endif
+#ifndef DNG_CTAS_PER_SM
 #define DNG_CTAS_PER_SM 1
+#endif
+#ifndef DNG_NLCAP
 #define DNG_NLCAP 2048			/* newline positions per pass */
+#endif
 #define DNG_SSLOTS_MIN 64		/* shared tally slots: as many as fit (pow2) */
 #define DNG_SSLOTS_MAX 4096
 #define DNG_FASTMAX 16384		/* longest line the lock-step automaton takes */
@@ -394,14 +398,17 @@ struct TmplSmem {
 	u32 ra;			/* record start */
 	u32 nodes, leaves, pool;
 
+	/* successive unaligned words; the aligned word after the one being
+	 * consumed is always already in flight, so a scan loop does not wait
+	 * for shared memory between its iterations */
 	struct Cur {
-		u32 wa, w0, sh;
+		u32 wa, w0, w1, sh;
 		__device__ __forceinline__ u32 next()
 		{
-			wa += 4;
-			const u32 w1 = lds32(wa);
 			const u32 d = __funnelshift_r(w0, w1, sh);
 			w0 = w1;
+			wa += 4;
+			w1 = lds32(wa);
 			return d;
 		}
 	};
@@ -410,8 +417,9 @@ struct TmplSmem {
 		Cur c;
 		const u32 a = ra + off;
 		c.sh = (a & 3) * 8;
-		c.wa = a & ~3u;
-		c.w0 = lds32(c.wa);
+		c.wa = (a & ~3u) + 4;
+		c.w0 = lds32(c.wa - 4);
+		c.w1 = lds32(c.wa);
 		return c;
 	}
 	__device__ __forceinline__ u32 byte(u32 off) const
@@ -430,9 +438,12 @@ struct TmplSmem {
 		q.x = v.x; q.y = v.y; q.z = v.z; q.w = v.w;
 		return q;
 	}
-	__device__ __forceinline__ u32 lit(u32 off) const
+	__device__ __forceinline__ TQuad lit2(u32 off) const
 	{
-		return lds32(pool + off);
+		const uint4 v = lds128(pool + off);
+		TQuad q;
+		q.x = v.x; q.y = v.y; q.z = v.z; q.w = v.w;
+		return q;
 	}
 	__device__ __forceinline__ u32 leaf(u32 i) const
 	{
@@ -559,6 +570,197 @@ __device__ __noinline__ void scan_one_global(const u8 *rec, u32 len,
 	scan_one(rec, len, P, stab, gt, C, mctr);
 }
 
+/*
+ * What both kernels know while they walk the records of one staged window
+ * (a tile of the CTA-wide kernel, a chunk of the per-warp kernel).
+ */
+struct WinCtx {
+	const ScanArgs &a;
+	const DevPlan &P;
+	STab stab;
+	TmplSmem tm;
+	LocalCounters &C;
+	u32 *mctr;
+	u32 &ntmpl, &nlong;
+	const u8 *sdata;		/* the window, in shared memory */
+	unsigned long long ws;		/* its offset in the input */
+	u32 wlen, lower;		/* valid bytes: [lower, wlen) */
+	u32 wlim;			/* last shared address a lane may read */
+	__device__ WinCtx(const ScanArgs &a_, const DevPlan &P_, STab st,
+	    const TmplSmem &tm_, LocalCounters &C_, u32 *mc, u32 &nt, u32 &nl)
+	    : a(a_), P(P_), stab(st), tm(tm_), C(C_), mctr(mc), ntmpl(nt),
+	    nlong(nl), sdata(nullptr), ws(0), wlen(0), lower(0), wlim(0) {}
+};
+
+/*
+ * One record per lane, the window's bytes [beg, end) (`end` is its newline).
+ * Phase 0 tries the template trie and returns true for a record it did not
+ * take (the caller queues it); phase 1 runs the lock-step byte automaton and
+ * its fallbacks.  Every lane of the warp must call this (have = false for
+ * lanes without a record): both matchers keep the warp in lock step.
+ */
+__device__ __forceinline__ bool scan_record(WinCtx &w, u32 phase, bool have,
+    bool islong, u32 beg, u32 end)
+{
+	const DevPlan &P = w.P;
+	const HotPlan &H = P.hot;
+	const u8 *sdata = w.sdata;
+	const u32 wlen = w.wlen;
+	LocalCounters &C = w.C;
+	const u32 len = end - beg;
+	RecState R;
+	bool parsed = false, failed = false;
+	const u8 *rec = sdata;
+	if (phase == 0) {
+		/* newline-terminated lines inside the window */
+		const bool elig = have && !islong && end < wlen &&
+		    len <= TMPL_MAX_LINE;
+		rec = sdata + beg;
+		w.tm.ra = smem_u32(rec);
+		parsed = tmpl_match(w.tm, len, R, elig);
+		if (parsed) {
+			C.lines++;
+			w.ntmpl++;
+		} else {
+			failed = have;
+		}
+	} else {
+		/*
+		 * Lock-step fast path: every lane steps the plan's byte
+		 * automaton over its own record; lanes without a (short,
+		 * newline-terminated) record idle in the absorbing FIN state.
+		 */
+		const bool fast = have && !islong && H.fast.ok &&
+		    len <= DNG_FASTMAX && end < wlen;
+		FastState fs;
+		fast_init(fs);
+		if (!fast)
+			fs.state = FS_FIN;
+		rec = sdata + (fast ? beg : 0);
+		u32 trip = __reduce_max_sync(0xffffffffu, fast ? len + 1 : 0);
+		/*
+		 * Four bytes per round: one aligned 32-bit shared load (+
+		 * funnel shift for the record's byte alignment) and four
+		 * independent class lookups are issued up front; only the
+		 * state transition itself is a dependent chain.
+		 */
+		{
+			const u32 ra = smem_u32(rec);
+			const u32 sh = (ra & 3) * 8;
+			u32 wa = ra & ~3u;
+			/* lanes idling past their own line while a neighbour
+			 * finishes a longer one must not run off the staged
+			 * window */
+			const u32 wlim = w.wlim;
+			u32 w0 = lds32(wa);
+			const u32 clsb = smem_u32(H.fast.cls);
+			const u32 trb = smem_u32(H.trans);
+			const u32 stride = H.fast.stride;
+			for (u32 i = 0; i < trip; i += 4) {
+				wa = min(wa + 4, wlim);
+				u32 w1 = lds32(wa);
+				u32 wd = __funnelshift_r(w0, w1, sh);
+				w0 = w1;
+				u32 c0 = lds8(clsb + (wd & 0xff));
+				u32 c1 = lds8(clsb + ((wd >> 8) & 0xff));
+				u32 c2 = lds8(clsb + ((wd >> 16) & 0xff));
+				u32 c3 = lds8(clsb + (wd >> 24));
+				FAST_STEP(c0, i);
+				FAST_STEP(c1, i + 1);
+				FAST_STEP(c2, i + 2);
+				FAST_STEP(c3, i + 3);
+			}
+		}
+		if (fast && fs.state == FS_FIN) {
+			C.lines++;
+			fast_finish(rec, fs, R);
+			parsed = true;
+		} else if (fast && fs.state == FS_ERR) {
+			C.lines++;
+			C.invalid_json++;
+		} else if (have && !islong) {
+			scan_one_shared(sdata + beg, len, P, w.stab, w.a.tab, C,
+			    w.mctr);
+		} else if (have) {
+			/* the line began before the staged window: find its
+			 * start in HBM and parse it from there */
+			unsigned long long q = w.ws + w.lower;
+			while (q > w.a.start && w.a.data[q - 1] != '\n')
+				q--;
+			w.nlong++;
+			scan_one_global(w.a.data + q,
+			    (u32)min((unsigned long long)DNG_MAXREC,
+			    w.ws + end - q), P, w.stab, w.a.tab, C, w.mctr);
+		}
+	}
+	if (parsed)
+		scan_tail(rec, len, P, R, w.stab, w.a.tab, C, w.mctr);
+	return failed;
+}
+
+/* end of a kernel: shared tally cache -> global table, counters -> global */
+__device__ __forceinline__ void scan_epilogue(const ScanArgs &a,
+    const DevPlan &P, const STab &stab, const LocalCounters &C,
+    const u32 *s_mctr, u32 nlong, u32 ntmpl)
+{
+	const u32 tid = threadIdx.x, lane = tid & 31;
+	__syncthreads();
+	for (u32 i = tid; i < a.s1slots; i += DNG_NT) {
+		const SSlot1 *s = &stab.s1[i];
+		if (s->tag != 0 && s->count)
+			global_add(a.tab, key_hash_words(s->key, s->klen),
+			    (const u8 *)s->key, s->klen,
+			    (unsigned long long)s->count);
+	}
+	for (u32 i = tid; i < a.sslots; i += DNG_NT) {
+		const SSlot *s = &stab.s[i];
+		if (s->tag != 0 && s->gidx1 != 0 && s->gidx1 != 0xffffffffu &&
+		    s->count)
+			atomicAdd(&a.tab.entries[s->gidx1 - 1].count,
+			    (unsigned long long)s->count);
+	}
+
+	if (P.nmetrics > 1) {
+		for (u32 k = 0; k < (u32)(P.nmetrics - 1) * MCTR_PER; k++) {
+			u32 v = s_mctr[k];
+			for (int d = 16; d > 0; d >>= 1)
+				v += __shfl_xor_sync(0xffffffffu, v, d);
+			if (lane == 0 && v)
+				atomicAdd(&a.counters[NCTR + k],
+				    (unsigned long long)v);
+		}
+	}
+
+	/* counters: warp reduce, one atomic per warp per counter */
+	u32 vals[NCTR];
+	for (int k = 0; k < NCTR; k++)
+		vals[k] = 0;
+	vals[CTR_LINES] = C.lines;
+	vals[CTR_INVALID_JSON] = C.invalid_json;
+	vals[CTR_INVALID_POINT] = C.invalid_point;
+	vals[CTR_DS_FILTERED] = C.ds_filtered;
+	vals[CTR_DS_FAILED] = C.ds_failedeval;
+	vals[CTR_USER_FILTERED] = C.user_filtered;
+	vals[CTR_USER_FAILED] = C.user_failedeval;
+	vals[CTR_SYNTH_UNDEF] = C.synth_undef;
+	vals[CTR_SYNTH_BADDATE] = C.synth_baddate;
+	vals[CTR_TIME_FILTERED] = C.time_filtered;
+	vals[CTR_TIME_FAILED] = C.time_failedeval;
+	vals[CTR_AGGR] = C.aggr;
+	vals[CTR_SLOW] = C.slow;
+	vals[CTR_UNSUPPORTED] = C.unsupported;
+	vals[CTR_LONG] = nlong;
+	vals[CTR_TMPL] = ntmpl;
+#pragma unroll
+	for (int k = 0; k <= CTR_TMPL; k++) {
+		u32 v = vals[k];
+		for (int d = 16; d > 0; d >>= 1)
+			v += __shfl_xor_sync(0xffffffffu, v, d);
+		if (lane == 0 && v)
+			atomicAdd(&a.counters[k], (unsigned long long)v);
+	}
+}
+
 /* ---- the kernel ------------------------------------------------------------ */
 
 __global__ void __launch_bounds__(DNG_NT, DNG_CTAS_PER_SM)
@@ -630,8 +832,19 @@ scan_kernel(const ScanArgs a)
 	C.unsupported = 0;
 	u32 nlong = 0;
 	u32 parity = 0;
+	WinCtx w(a, P, stab, tm, C, s_mctr, ntmpl, nlong);
+	w.sdata = sdata;
+	w.wlim = smem_u32(sdata) + DNG_PRELAP + DNG_TILE + DNG_SLACK;
 
+#ifdef DNG_PROFILE_PHASES
+	long long pf_load = 0, pf_index = 0, pf_busy = 0, pf_phase = 0;
+	long long pf_total = 0, pf_n = 0;
+#define PF_CLK() clock64()
+#endif
 	for (u32 tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+#ifdef DNG_PROFILE_PHASES
+		const long long pf_t0 = PF_CLK();
+#endif
 		const unsigned long long g0 = (unsigned long long)tile * DNG_TILE;
 		const unsigned long long ws = g0 >= DNG_PRELAP ?
 		    g0 - DNG_PRELAP : 0;
@@ -661,9 +874,17 @@ scan_kernel(const ScanArgs a)
 			parity ^= 1;
 		}
 		__syncthreads();
+#ifdef DNG_PROFILE_PHASES
+		const long long pf_t1 = PF_CLK();
+		pf_load += pf_t1 - pf_t0;
+		long long pf_rec = 0;
+#endif
 
 		/* lowest window offset that holds valid input */
 		const u32 lower = a.start > ws ? (u32)(a.start - ws) : 0;
+		w.ws = ws;
+		w.wlen = wlen;
+		w.lower = lower;
 		/* this thread's slice of the tile, 16-byte words */
 		const u32 CH = DNG_TILE / DNG_NT;
 		u32 c0 = off0 + tid * CH, c1 = c0 + CH;
@@ -765,6 +986,9 @@ scan_kernel(const ScanArgs a)
 			 * templates, all records) go through the byte automaton
 			 * and its fallbacks, densely packed into warps again.
 			 */
+#ifdef DNG_PROFILE_PHASES
+			const long long pf_t2 = PF_CLK();
+#endif
 			for (u32 phase = use_tmpl ? 0 : 1; phase < 2; phase++) {
 			const u32 nn = (phase == 1 && use_tmpl) ? s_nfail : n;
 			for (u32 rb = 0; rb < nn; rb += DNG_NT) {
@@ -793,169 +1017,333 @@ scan_kernel(const ScanArgs a)
 							islong = true;
 					}
 				}
-				const u32 len = end - beg;
-				RecState R;
-				bool parsed = false;
-				const u8 *rec = sdata;
-				if (phase == 0) {
-					/* newline-terminated lines inside the window */
-					const bool elig = have && !islong && end < wlen &&
-					    len <= TMPL_MAX_LINE;
-					rec = sdata + beg;
-					tm.ra = smem_u32(rec);
-					parsed = tmpl_match(tm, len, R, elig);
-					if (parsed) {
-						C.lines++;
-						ntmpl++;
-					} else if (have) {
-						failq[atomicAdd(&s_nfail, 1u)] = (u16)r;
-					}
-				} else {
-				/*
-				 * Lock-step fast path: every lane steps the plan's
-				 * byte automaton over its own record; lanes without
-				 * a (short, newline-terminated) record idle in the
-				 * absorbing FIN state.
-				 */
-				const bool fast = have && !islong && H.fast.ok &&
-				    len <= DNG_FASTMAX && end < wlen;
-				FastState fs;
-				fast_init(fs);
-				if (!fast)
-					fs.state = FS_FIN;
-				rec = sdata + (fast ? beg : 0);
-				u32 trip = __reduce_max_sync(0xffffffffu,
-				    fast ? len + 1 : 0);
-				/*
-				 * Four bytes per round: one aligned 32-bit shared
-				 * load (+ funnel shift for the record's byte
-				 * alignment) and four independent class lookups are
-				 * issued up front; only the state transition itself
-				 * is a dependent chain.
-				 */
-				{
-					const u32 ra = smem_u32(rec);
-					const u32 sh = (ra & 3) * 8;
-					u32 wa = ra & ~3u;
-					/* lanes idling past their own line while a
-					 * neighbour finishes a longer one must not
-					 * run off the staged window */
-					const u32 wlim = smem_u32(sdata) +
-					    DNG_PRELAP + DNG_TILE + DNG_SLACK;
-					u32 w0 = lds32(wa);
-					const u32 clsb = smem_u32(H.fast.cls);
-					const u32 trb = smem_u32(H.trans);
-					const u32 stride = H.fast.stride;
-					for (u32 i = 0; i < trip; i += 4) {
-						wa = min(wa + 4, wlim);
-						u32 w1 = lds32(wa);
-						u32 w = __funnelshift_r(w0, w1, sh);
-						w0 = w1;
-						u32 c0 = lds8(clsb + (w & 0xff));
-						u32 c1 = lds8(clsb + ((w >> 8) & 0xff));
-						u32 c2 = lds8(clsb + ((w >> 16) & 0xff));
-						u32 c3 = lds8(clsb + (w >> 24));
-						FAST_STEP(c0, i);
-						FAST_STEP(c1, i + 1);
-						FAST_STEP(c2, i + 2);
-						FAST_STEP(c3, i + 3);
-					}
-				}
-				if (fast && fs.state == FS_FIN) {
-					C.lines++;
-					fast_finish(rec, fs, R);
-					parsed = true;
-				} else if (fast && fs.state == FS_ERR) {
-					C.lines++;
-					C.invalid_json++;
-				} else if (have && !islong) {
-					scan_one_shared(sdata + beg, len, P, stab,
-					    a.tab, C, s_mctr);
-				} else if (have) {
-					/* the line began before the staged
-					 * window: find its start in HBM and
-					 * parse it from there */
-					unsigned long long q = ws + lower;
-					while (q > a.start &&
-					    a.data[q - 1] != '\n')
-						q--;
-					nlong++;
-					scan_one_global(a.data + q,
-					    (u32)min((unsigned long long)
-					    DNG_MAXREC, ws + end - q), P, stab,
-					    a.tab, C, s_mctr);
-				}
-				}
-				if (parsed)
-					scan_tail(rec, len, P, R, stab, a.tab, C,
-					    s_mctr);
+				const bool failed = scan_record(w, phase, have, islong,
+				    beg, end);
+				if (failed)
+					failq[atomicAdd(&s_nfail, 1u)] = (u16)r;
 			}
+#ifdef DNG_PROFILE_PHASES
+			if (phase == 0)
+				pf_busy += PF_CLK() - pf_t2;
+#endif
 			__syncthreads();
 			}
+#ifdef DNG_PROFILE_PHASES
+			pf_phase += PF_CLK() - pf_t2;
+			pf_rec += PF_CLK() - pf_t2;
+#endif
 			__syncthreads();
 			if (tid == 0)
 				s_prev = nlpos[n - 1];
 			__syncthreads();
 		}
 		__syncthreads();
+#ifdef DNG_PROFILE_PHASES
+		pf_total += PF_CLK() - pf_t0;
+		pf_index += PF_CLK() - pf_t1 - pf_rec;
+		pf_n++;
+#endif
 	}
+#ifdef DNG_PROFILE_PHASES
+	if (lane == 0) {
+		atomicAdd(&a.counters[16], (unsigned long long)pf_busy);
+		atomicAdd(&a.counters[17], (unsigned long long)pf_phase);
+		atomicAdd(&a.counters[18], (unsigned long long)pf_n);
+		atomicAdd(&a.counters[19], (unsigned long long)pf_load);
+		atomicAdd(&a.counters[20], (unsigned long long)pf_index);
+		atomicAdd(&a.counters[21], (unsigned long long)pf_total);
+	}
+#endif
 
-	/* flush the shared table into the global one */
+	scan_epilogue(a, P, stab, C, s_mctr, nlong, ntmpl);
+}
+
+/* ---- the per-warp kernel ---------------------------------------------------- */
+
+/*
+ * Same algorithm, different geometry: every WARP stages its own small chunk of
+ * the input (TMA into a private slice of shared memory, its own mbarrier),
+ * finds the newlines in it with warp shuffles and walks its ~30 records, with
+ * no CTA-wide barrier anywhere in the loop.  In the CTA-wide kernel above a
+ * tile is one batch of records per warp between barriers, so half the warps of
+ * an SM are parked at a barrier at any time; here all of them always have
+ * work, which is what hides the latencies of the record matchers.
+ *
+ * A chunk owns the records that END in it and stages DNG_W_PRELAP bytes before
+ * itself for the record that straddles its start; lines longer than that take
+ * the HBM path, so the host picks this kernel only for input whose (sampled)
+ * lines are short (DNG_W_MAXLINE) and the CTA-wide kernel otherwise.
+ */
+#define DNG_W_SLICE 208				/* bytes per lane: 13 x 16 */
+#define DNG_W_CHUNK (32 * DNG_W_SLICE)		/* 6656 bytes owned per step */
+#define DNG_W_PRELAP 1024
+#define DNG_W_SLACK 64
+#define DNG_W_NLCAP 64				/* newline positions per pass */
+#define DNG_W_MAXLINE 768
+#define DNG_NW (DNG_NT / 32)
+
+static constexpr size_t SMEM_W_BUF = DNG_W_PRELAP + DNG_W_CHUNK + DNG_W_SLACK;
+/* per warp: window, newline positions, fallback queue, mbarrier */
+static constexpr size_t SMEM_W_WARP = SMEM_W_BUF + 4 * DNG_W_NLCAP +
+    DNG_W_NLCAP + 16;
+static constexpr size_t SMEM_W_FIXED = DNG_NW * SMEM_W_WARP + 128;
+
+__global__ void __launch_bounds__(DNG_NT, 1)
+scan_kernel_w(const ScanArgs a)
+{
+	extern __shared__ __align__(128) u8 smem[];
+	DevPlan *sp = (DevPlan *)smem;
+	const u32 tab1_bytes = a.s1slots * (u32)sizeof (SSlot1);
+	const u32 tab_bytes = tab1_bytes + a.sslots * (u32)sizeof (SSlot);
+	STab stab;
+	const u32 fixed_bytes = a.plan_bytes + a.tmpl_bytes;
+	stab.s1 = (SSlot1 *)(smem + fixed_bytes);
+	stab.s = (SSlot *)(smem + fixed_bytes + tab1_bytes);
+	stab.mask1 = a.s1slots - 1;
+	stab.mask = a.sslots - 1;
+	u32 s_mctr[(MAX_METRICS - 1) * MCTR_PER];	/* thread-local */
+	for (int k = 0; k < (MAX_METRICS - 1) * MCTR_PER; k++)
+		s_mctr[k] = 0;
+
+	const u32 tid = threadIdx.x;
+	const u32 lane = tid & 31, wid = tid >> 5;
+	/* this warp's private slice */
+	u8 *sdata = smem + fixed_bytes + tab_bytes + wid * SMEM_W_WARP;
+	u32 *nlpos = (u32 *)(sdata + SMEM_W_BUF);
+	u8 *failq = (u8 *)(nlpos + DNG_W_NLCAP);
+	u64 *mbar = (u64 *)(failq + DNG_W_NLCAP);
+
+	{	/* plan -> shared, clear the table */
+		const uint4 *src = (const uint4 *)a.plan;
+		uint4 *dst = (uint4 *)sp;
+		for (u32 i = tid; i < a.plan_bytes / 16; i += DNG_NT)
+			dst[i] = src[i];
+		const uint4 *tsrc = (const uint4 *)a.tmpl;
+		uint4 *tdst = (uint4 *)(smem + a.plan_bytes);
+		for (u32 i = tid; i < a.tmpl_bytes / 16; i += DNG_NT)
+			tdst[i] = tsrc[i];
+		uint4 z = make_uint4(0, 0, 0, 0);
+		uint4 *tz = (uint4 *)stab.s1;
+		for (u32 i = tid; i < tab_bytes / 16; i += DNG_NT)
+			tz[i] = z;
+		if (lane == 0)
+			mbar_init(mbar, 1);
+	}
 	__syncthreads();
-	for (u32 i = tid; i < a.s1slots; i += DNG_NT) {
-		const SSlot1 *s = &stab.s1[i];
-		if (s->tag != 0 && s->count)
-			global_add(a.tab, key_hash_words(s->key, s->klen),
-			    (const u8 *)s->key, s->klen,
-			    (unsigned long long)s->count);
-	}
-	for (u32 i = tid; i < a.sslots; i += DNG_NT) {
-		const SSlot *s = &stab.s[i];
-		if (s->tag != 0 && s->gidx1 != 0 && s->gidx1 != 0xffffffffu &&
-		    s->count)
-			atomicAdd(&a.tab.entries[s->gidx1 - 1].count,
-			    (unsigned long long)s->count);
-	}
+	const DevPlan &P = *sp;
 
-	if (P.nmetrics > 1) {
-		for (u32 k = 0; k < (u32)(P.nmetrics - 1) * MCTR_PER; k++) {
-			u32 v = s_mctr[k];
-			for (int d = 16; d > 0; d >>= 1)
-				v += __shfl_xor_sync(0xffffffffu, v, d);
-			if (lane == 0 && v)
-				atomicAdd(&a.counters[NCTR + k],
-				    (unsigned long long)v);
+	const bool use_tmpl = a.tmpl_bytes != 0;
+	TmplSmem tm;
+	tm.ra = 0;
+	tm.nodes = smem_u32(smem + a.plan_bytes) + (u32)sizeof (THdr);
+	tm.leaves = tm.pool = 0;
+	if (use_tmpl) {
+		const THdr *th = (const THdr *)(smem + a.plan_bytes);
+		tm.leaves = smem_u32(smem + a.plan_bytes) + th->leaf_off;
+		tm.pool = smem_u32(smem + a.plan_bytes) + th->pool_off;
+	}
+	u32 ntmpl = 0;
+
+	LocalCounters C;
+	C.lines = C.invalid_json = C.invalid_point = 0;
+	C.ds_filtered = C.ds_failedeval = C.user_filtered = 0;
+	C.user_failedeval = C.synth_undef = C.synth_baddate = 0;
+	C.time_filtered = C.time_failedeval = C.aggr = C.slow = 0;
+	C.unsupported = 0;
+	u32 nlong = 0;
+	u32 parity = 0;
+	WinCtx w(a, P, stab, tm, C, s_mctr, ntmpl, nlong);
+	w.sdata = sdata;
+	w.wlim = smem_u32(sdata) + (u32)SMEM_W_BUF;
+	const u32 ltmask = (1u << lane) - 1;
+
+	const u32 nwarps = gridDim.x * DNG_NW;
+	for (u32 ch = blockIdx.x * DNG_NW + wid; ch < a.ntiles; ch += nwarps) {
+		const unsigned long long g0 = (unsigned long long)ch * DNG_W_CHUNK;
+		const unsigned long long ws = g0 >= DNG_W_PRELAP ?
+		    g0 - DNG_W_PRELAP : 0;
+		unsigned long long we = g0 + DNG_W_CHUNK;
+		if (we > a.nbytes)
+			we = a.nbytes;
+		const u32 wlen = (u32)(we - ws);
+		const u32 bulk = wlen & ~15u;
+		const u32 off0 = (u32)(g0 - ws);	/* chunk start in window */
+
+		__syncwarp();		/* the previous chunk is done with */
+		if (lane == 0 && bulk) {
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			mbar_expect_tx(mbar, bulk);
+			tma_load_1d(sdata, a.data + ws, bulk, mbar);
+			/* start pulling this warp's next chunk into L2 */
+			unsigned long long nx = g0 +
+			    (unsigned long long)nwarps * DNG_W_CHUNK;
+			if (nx + DNG_W_CHUNK <= a.nbytes)
+				asm volatile("cp.async.bulk.prefetch.L2.global "
+				    "[%0], %1;" :: "l"(a.data + nx),
+				    "r"((u32)DNG_W_CHUNK) : "memory");
+		}
+		for (u32 i = bulk + lane; i < wlen; i += 32)
+			sdata[i] = a.data[ws + i];
+		if (bulk) {
+			mbar_wait(mbar, parity);
+			parity ^= 1;
+		}
+		__syncwarp();
+
+		/* lowest window offset that holds valid input */
+		const u32 lower = a.start > ws ? (u32)(a.start - ws) : 0;
+		w.ws = ws;
+		w.wlen = wlen;
+		w.lower = lower;
+		/* this lane's slice of the chunk, 16-byte words */
+		u32 c0 = off0 + lane * DNG_W_SLICE, c1 = c0 + DNG_W_SLICE;
+		if (c1 > wlen)
+			c1 = wlen;
+		u32 cnt = 0;
+		u32 hot = 0;		/* bit j: 16-byte word j holds a newline */
+		for (u32 p = c0; p < c1; p += 16) {
+			uint4 v = *(const uint4 *)(sdata + p);
+			u32 m0 = nl_mask(v.x), m1 = nl_mask(v.y);
+			u32 m2 = nl_mask(v.z), m3 = nl_mask(v.w);
+			if (p + 16 > c1 || p < lower) {
+				/* partial word: keep only bytes in [lower, c1) */
+				m0 &= byte_range_mask(p, lower, c1);
+				m1 &= byte_range_mask(p + 4, lower, c1);
+				m2 &= byte_range_mask(p + 8, lower, c1);
+				m3 &= byte_range_mask(p + 12, lower, c1);
+			}
+			u32 k = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+			cnt += k;
+			if (k)
+				hot |= 1u << ((p - c0) >> 4);
+		}
+		/* an unterminated final line ends at a virtual newline */
+		const bool vnl = a.final && we == a.nbytes && lane == 31 &&
+		    a.nbytes > a.start && wlen > 0 && wlen > lower &&
+		    sdata[wlen - 1] != '\n';
+		if (vnl)
+			cnt++;
+
+		/* warp exclusive scan of cnt */
+		u32 incl = cnt;
+		for (int d = 1; d < 32; d <<= 1) {
+			u32 y = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= (u32)d)
+				incl += y;
+		}
+		const u32 mybase = incl - cnt;
+		const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+		if (total == 0)
+			continue;
+
+		/*
+		 * Where the first record starts: after the last newline of the
+		 * pre-lap [lower, start0), which the lanes search together (32
+		 * bytes each, nearest the chunk first).
+		 */
+		const u32 start0 = off0 < lower ? lower : off0;
+		u32 beg0 = lower;
+		bool islong0 = false;
+		{
+			u32 mine = 0;		/* 1 + position of a newline */
+			if (off0 > lower && off0 >= 32 * (lane + 1)) {
+				const u32 lo = off0 - 32 * (lane + 1);
+				const uint4 v0 = *(const uint4 *)(sdata + lo);
+				const uint4 v1 = *(const uint4 *)(sdata + lo + 16);
+				const u32 wd[8] = { v0.x, v0.y, v0.z, v0.w,
+				    v1.x, v1.y, v1.z, v1.w };
+#pragma unroll
+				for (int j = 7; j >= 0; j--) {
+					u32 m = nl_mask(wd[j]);
+					if (lo < lower)
+						m &= byte_range_mask(lo + 4 * j,
+						    lower, off0);
+					if (m && !mine)
+						mine = lo + 4 * j +
+						    ((31 - __clz(m)) >> 3) + 1;
+				}
+			}
+			const u32 best = __reduce_max_sync(0xffffffffu, mine);
+			if (best)
+				beg0 = best;
+			else
+				islong0 = ws + lower > a.start &&
+				    (lower == 0 || sdata[lower - 1] != '\n');
+		}
+
+		u32 prev_end = 0;	/* newline that closed the previous pass */
+		for (u32 pass = 0; pass < total; pass += DNG_W_NLCAP) {
+			/* write this pass's newline positions, in order */
+			u32 idx = mybase;
+			if (idx < pass + DNG_W_NLCAP && idx + cnt > pass) {
+				for (u32 hm = hot; hm; hm &= hm - 1) {
+					const u32 p = c0 + ((__ffs(hm) - 1) << 4);
+					uint4 v = *(const uint4 *)(sdata + p);
+					u32 mm[4] = { nl_mask(v.x), nl_mask(v.y),
+					    nl_mask(v.z), nl_mask(v.w) };
+					const bool partial = p + 16 > c1 || p < lower;
+#pragma unroll
+					for (u32 q = 0; q < 4; q++) {
+						u32 m = mm[q];
+						if (partial)
+							m &= byte_range_mask(p + 4 * q,
+							    lower, c1);
+						while (m) {
+							u32 b = (__ffs(m) - 1) >> 3;
+							m &= m - 1;
+							if (idx >= pass &&
+							    idx < pass + DNG_W_NLCAP)
+								nlpos[idx - pass] =
+								    p + 4 * q + b;
+							idx++;
+						}
+					}
+				}
+				if (vnl && idx >= pass && idx < pass + DNG_W_NLCAP)
+					nlpos[idx - pass] = wlen;
+			}
+			__syncwarp();
+			u32 n = total - pass;
+			if (n > DNG_W_NLCAP)
+				n = DNG_W_NLCAP;
+			u32 nfail = 0;
+			/* phase 0: templates; phase 1: what they did not take
+			 * (or, without templates, everything) */
+			for (u32 phase = use_tmpl ? 0 : 1; phase < 2; phase++) {
+				const u32 nn = (phase == 1 && use_tmpl) ? nfail : n;
+				for (u32 rb = 0; rb < nn; rb += 32) {
+					const bool have = rb + lane < nn;
+					u32 r = rb + lane;
+					if (have && phase == 1 && use_tmpl)
+						r = failq[r];
+					u32 end = 0, beg = 0;
+					bool islong = false;
+					if (have) {
+						end = nlpos[r];
+						if (r > 0) {
+							beg = nlpos[r - 1] + 1;
+						} else if (pass > 0) {
+							beg = prev_end + 1;
+						} else {
+							beg = beg0 < end ? beg0 : end;
+							islong = islong0;
+						}
+					}
+					const bool failed = scan_record(w, phase, have,
+					    islong, beg, end);
+					const u32 fm = __ballot_sync(0xffffffffu, failed);
+					if (failed)
+						failq[nfail + __popc(fm & ltmask)] = (u8)r;
+					nfail += __popc(fm);
+				}
+				__syncwarp();
+			}
+			prev_end = nlpos[n - 1];
+			__syncwarp();
 		}
 	}
 
-	/* counters: warp reduce, one atomic per warp per counter */
-	u32 vals[NCTR];
-	for (int k = 0; k < NCTR; k++)
-		vals[k] = 0;
-	vals[CTR_LINES] = C.lines;
-	vals[CTR_INVALID_JSON] = C.invalid_json;
-	vals[CTR_INVALID_POINT] = C.invalid_point;
-	vals[CTR_DS_FILTERED] = C.ds_filtered;
-	vals[CTR_DS_FAILED] = C.ds_failedeval;
-	vals[CTR_USER_FILTERED] = C.user_filtered;
-	vals[CTR_USER_FAILED] = C.user_failedeval;
-	vals[CTR_SYNTH_UNDEF] = C.synth_undef;
-	vals[CTR_SYNTH_BADDATE] = C.synth_baddate;
-	vals[CTR_TIME_FILTERED] = C.time_filtered;
-	vals[CTR_TIME_FAILED] = C.time_failedeval;
-	vals[CTR_AGGR] = C.aggr;
-	vals[CTR_SLOW] = C.slow;
-	vals[CTR_UNSUPPORTED] = C.unsupported;
-	vals[CTR_LONG] = nlong;
-	vals[CTR_TMPL] = ntmpl;
-#pragma unroll
-	for (int k = 0; k <= CTR_TMPL; k++) {
-		u32 v = vals[k];
-		for (int d = 16; d > 0; d >>= 1)
-			v += __shfl_xor_sync(0xffffffffu, v, d);
-		if (lane == 0 && v)
-			atomicAdd(&a.counters[k], (unsigned long long)v);
-	}
+	scan_epilogue(a, P, stab, C, s_mctr, nlong, ntmpl);
 }
 
 /* gather occupied entries: out[i] = {koff-1, klen, count} */

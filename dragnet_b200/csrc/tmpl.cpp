@@ -269,7 +269,7 @@ struct Trie {
 				hit = (int)nodes.size();
 				nodes.push_back(b);
 				nodes[cur].kids.push_back(hit);
-				pool += (g.lit.size() + 3) / 4 * 4 + 4;
+				pool += (g.lit.size() + 7) / 8 * 16;
 			} else {
 				BNode &b = nodes[hit];
 				if (g.cap) {
@@ -410,10 +410,16 @@ void tmpl_build(const std::vector<TCandidate> &cands,
 			memset(&o, 0, sizeof (o));
 			o.lit = (u16)pool.size();
 			o.len = (u16)b.lit.size();
-			pool += b.lit;
-			pool.append((4 - pool.size() % 4) % 4 + 4, '\0');
-			u32 rem = (u32)b.lit.size() % 4;
-			o.lastmask = rem ? (1u << (8 * rem)) - 1 : 0xffffffffu;
+			for (size_t k = 0; k < b.lit.size(); k += 4) {
+				u32 v = 0, mk = 0;
+				for (size_t j = 0; j < 4 && k + j < b.lit.size(); j++) {
+					v |= (u32)(u8)b.lit[k + j] << (8 * j);
+					mk |= 0xffu << (8 * j);
+				}
+				pool.append((const char *)&v, 4);
+				pool.append((const char *)&mk, 4);
+			}
+			pool.append((16 - pool.size() % 16) % 16, '\0');
 			o.kind = b.kind;
 			o.cap = b.cap;
 			o.poscap = b.poscap;

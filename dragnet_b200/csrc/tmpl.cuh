@@ -73,21 +73,27 @@ DNG_HD u32 low_flag_byte(u32 m)
 template <class M>
 DNG_HD bool tmpl_match(M &m, u32 len, RecState &R, bool active)
 {
-	u32 p = 0, node = 0;
+	u32 p = 0;
 	bool matched = false;
+	TQuad nd = m.node(0);
 	while (DNG_WARP_ANY(active)) {
 		if (active) {
-		const TQuad nd = m.node(node);
+		/* the likely successor is fetched while this node is matched */
+		const u32 succ = nd.y & 0xffff;
+		const TQuad nx = m.node(succ & TN_LEAF ? 0 : succ);
 		const u32 lit = nd.x & 0xffff, L = nd.x >> 16;
 		bool ok = p + L <= len;
 		if (ok && L) {
-			/* whole words, then the last one under the node's mask */
+			/* eight bytes a step against (value, mask) word pairs:
+			 * the literal's padding is masked out, so no tail case */
 			typename M::Cur c = m.cursor(p);
-			const u32 last = (L - 1) & ~3u;
 			u32 diff = 0;
-			for (u32 k = 0; k < last; k += 4)
-				diff |= c.next() ^ m.lit(lit + k);
-			diff |= (c.next() ^ m.lit(lit + last)) & nd.w;
+#pragma unroll 1
+			for (u32 k = 0; k < L; k += 8) {
+				const TQuad lq = m.lit2(lit + 2 * k);
+				const u32 d0 = c.next(), d1 = c.next();
+				diff |= ((d0 ^ lq.x) & lq.y) | ((d1 ^ lq.z) & lq.w);
+			}
 			ok = diff == 0;
 		}
 		u32 q = p + L;
@@ -169,8 +175,9 @@ DNG_HD bool tmpl_match(M &m, u32 len, RecState &R, bool active)
 		}
 		if (!ok) {
 			/* this node is not it: its next sibling, same place */
-			node = nd.y >> 16;
-			active = node != TN_NOALT;
+			const u32 alt = nd.y >> 16;
+			active = alt != TN_NOALT;
+			nd = m.node(active ? alt : 0);
 		} else {
 			const u32 pc = (nd.z >> 16) & 0xff;
 			const u32 cap = (nd.z >> 8) & 0xff;
@@ -180,15 +187,15 @@ DNG_HD bool tmpl_match(M &m, u32 len, RecState &R, bool active)
 			if (cap)
 				R.slots[cap - 1] = val;
 			p = q;
-			node = nd.y & 0xffff;
-			if (node & TN_LEAF) {
+			if (succ & TN_LEAF) {
 				active = false;
 				if (p == len) {
-					R.set_mask = m.leaf(node & 0x7fff);
+					R.set_mask = m.leaf(succ & 0x7fff);
 					R.flags = 0;
 					matched = true;
 				}
 			}
+			nd = nx;
 		}
 		}
 	}
@@ -218,9 +225,9 @@ struct TmplHostMem {
 		memcpy(&v, blob + sizeof (THdr) + 16 * (size_t)i, 16);
 		return v;
 	}
-	u32 lit(u32 off) const {
-		u32 v;
-		memcpy(&v, blob + ((const THdr *)blob)->pool_off + off, 4);
+	TQuad lit2(u32 off) const {
+		TQuad v;
+		memcpy(&v, blob + ((const THdr *)blob)->pool_off + off, 16);
 		return v;
 	}
 	u32 leaf(u32 i) const {

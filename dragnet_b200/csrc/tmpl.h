@@ -34,7 +34,9 @@ enum : u8 { TK_NONE = 0, TK_STR = 1, TK_BARE = 2 };
 enum : u16 { TN_LEAF = 0x8000, TN_NOALT = 0xffff };
 
 struct alignas(16) TNode {
-	u16 lit;	/* literal bytes: pool offset, 4-byte aligned */
+	u16 lit;	/* literal: pool offset (16-byte aligned) of ceil(len/8)
+			 * entries { value0, mask0, value1, mask1 }: eight literal
+			 * bytes as two little-endian words, padding masked out */
 	u16 len;	/* literal length (may be 0) */
 	u16 next;	/* node after the wildcard, or TN_LEAF | leaf */
 	u16 alt;	/* sibling to try if the literal differs, or TN_NOALT */
@@ -42,8 +44,7 @@ struct alignas(16) TNode {
 	u8 cap;		/* 1 + plan slot receiving the wildcard, or 0 */
 	u8 poscap;	/* 1 + plan slot receiving the container that opens at
 			 * the literal's first byte, or 0 */
-	u8 pad;
-	u32 lastmask;	/* bytes of the literal's last 32-bit word that count */
+	u8 pad[5];
 };
 
 struct alignas(16) THdr {
@@ -54,7 +55,7 @@ struct alignas(16) THdr {
 };
 
 enum : u32 {
-	TMPL_MAX_NODES = 448, TMPL_MAX_POOL = 6144, TMPL_MAX_LEAVES = 24,
+	TMPL_MAX_NODES = 448, TMPL_MAX_POOL = 12288, TMPL_MAX_LEAVES = 24,
 	TMPL_MAX_LINE = 4096,		/* longer lines are never templated */
 	TMPL_SAMPLE_BYTES = 256 * 1024
 };

@@ -9,7 +9,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdragnet_gpu.so')
+# DNG_LIB: another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get('DNG_LIB') or os.path.join(_HERE,
+                                                    'libdragnet_gpu.so')
 
 DNG_OK = 0
 ERRORS = {-1: 'EINVAL', -2: 'ENODEV', -3: 'ECUDA', -4: 'ENOMEM', -5: 'EIO',

@@ -16,6 +16,15 @@ from golden_harness import check_section  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=['auto', 'tile', 'warp'], autouse=True)
+def kernel_geometry(request, monkeypatch):
+    """Every case under both kernel geometries (CTA-wide tiles, per-warp
+    chunks) and under the library's own choice between them."""
+    monkeypatch.delenv('DNG_KERNEL', raising=False)
+    if request.param != 'auto':
+        monkeypatch.setenv('DNG_KERNEL', request.param)
+
+
 def gpu_engine(plan, files):
     from dragnet_b200 import datasource_gpu
     r = datasource_gpu.run_plan(plan, files=files)
