@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <map>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -45,6 +46,79 @@ size_t env_size(const char *name, size_t dflt)
 		return dflt;
 	return (size_t)strtoull(v, nullptr, 0);
 }
+
+/*
+ * Scan buffers (table, key arena, carry, H2D ring, pinned staging) have the
+ * same few sizes for every scan, and cudaMalloc / cudaMallocHost / cudaFree
+ * cost milliseconds each: destroyed scans park their buffers here and the
+ * next scan on that device takes them back.  Bounded (DNG_CACHE_BYTES, default
+ * 2 GiB per kind); dng_release_cached() empties it.
+ */
+struct BufCache {
+	std::mutex mu;
+	std::multimap<std::pair<int, size_t>, void *> idle;	/* (device|-1 host, bytes) */
+	std::map<void *, std::pair<int, size_t>> live;
+	size_t idle_dev = 0, idle_host = 0;
+};
+
+BufCache &buf_cache()
+{
+	static BufCache *c = new BufCache();	/* outlives static destructors */
+	return *c;
+}
+
+cudaError_t cached_alloc(int device, void **p, size_t n)
+{
+	BufCache &c = buf_cache();
+	{
+		std::lock_guard<std::mutex> g(c.mu);
+		auto it = c.idle.find(std::make_pair(device, n));
+		if (it != c.idle.end()) {
+			*p = it->second;
+			c.idle.erase(it);
+			(device < 0 ? c.idle_host : c.idle_dev) -= n;
+			c.live[*p] = std::make_pair(device, n);
+			return cudaSuccess;
+		}
+	}
+	cudaError_t e = device < 0 ? cudaMallocHost(p, n) : cudaMalloc(p, n);
+	if (e == cudaSuccess) {
+		std::lock_guard<std::mutex> g(c.mu);
+		c.live[*p] = std::make_pair(device, n);
+	}
+	return e;
+}
+
+void cached_free(void *p)
+{
+	if (!p)
+		return;
+	static const size_t limit = env_size("DNG_CACHE_BYTES", (size_t)2 << 30);
+	BufCache &c = buf_cache();
+	int device = 0;
+	{
+		std::lock_guard<std::mutex> g(c.mu);
+		auto it = c.live.find(p);
+		if (it == c.live.end())
+			return;
+		device = it->second.first;
+		size_t n = it->second.second;
+		c.live.erase(it);
+		size_t &idle = device < 0 ? c.idle_host : c.idle_dev;
+		if (idle + n <= limit) {
+			idle += n;
+			c.idle.insert(std::make_pair(std::make_pair(device, n), p));
+			return;
+		}
+	}
+	if (device < 0)
+		cudaFreeHost(p);
+	else
+		cudaFree(p);
+}
+
+#define DEV_ALLOC(s, p, n) cached_alloc((s)->device, (void **)(p), (n))
+#define HOST_ALLOC(p, n) cached_alloc(-1, (void **)(p), (n))
 
 void set_err(char *err, size_t errlen, const char *fmt, const char *a = "")
 {
@@ -85,6 +159,7 @@ struct dng_scan {
 	std::vector<cudaEvent_t> ev_pool;
 	double kernel_ms = 0;
 	uint64_t launches = 0, kernel_bytes = 0, bytes_fed = 0;
+	cudaEvent_t ev_init = nullptr;	/* setup enqueued by dng_scan_open */
 	bool finished = false;
 	/* record templates (tmpl.h), learned from the head of the input */
 	bool tmpl_enabled = true, tmpl_tried = false;
@@ -160,10 +235,18 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 		return 0;
 	size_t n = (size_t)std::min<unsigned long long>(nbytes - start,
 	    TMPL_SAMPLE_BYTES);
-	std::vector<u8> head(n);
-	CK(s, cudaMemcpyAsync(head.data(), data + start, n,
-	    cudaMemcpyDeviceToHost, s->stream));
+	/* pinned (and cached) so that the copy is a plain DMA */
+	u8 *hbuf = nullptr;
+	CK(s, HOST_ALLOC(&hbuf, TMPL_SAMPLE_BYTES));
+	struct Release {
+		u8 *p;
+		~Release() { cached_free(p); }
+	} release{hbuf};
+	CK(s, cudaMemcpyAsync(hbuf, data + start, n, cudaMemcpyDeviceToHost,
+	    s->stream));
 	CK(s, cudaStreamSynchronize(s->stream));
+	struct { u8 *p; u8 *data() const { return p; }
+	    u8 operator[](size_t i) const { return p[i]; } } head{hbuf};
 	if (s->kernel_pref == 0) {
 		/* short lines: every warp stages its own chunk (scan_kernel_w);
 		 * otherwise CTA-wide tiles, whose window holds long lines */
@@ -196,11 +279,13 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 	u32 *d_offs = nullptr;
 	TResolved *d_res = nullptr;
 	std::vector<TResolved> res(cands.size());
-	cudaError_t e = cudaMalloc(&d_lines, lines.size() + 16);
+	/* constant sizes, so that the buffer cache can hand them back */
+	cudaError_t e = DEV_ALLOC(s, &d_lines,
+	    (size_t)TMPL_MAX_LEAVES * (TMPL_MAX_LINE + 1) + 16);
 	if (e == cudaSuccess)
-		e = cudaMalloc(&d_offs, 2 * offs.size() * sizeof (u32));
+		e = DEV_ALLOC(s, &d_offs, 2 * (TMPL_MAX_LEAVES + 1) * sizeof (u32));
 	if (e == cudaSuccess)
-		e = cudaMalloc(&d_res, res.size() * sizeof (TResolved));
+		e = DEV_ALLOC(s, &d_res, TMPL_MAX_LEAVES * sizeof (TResolved));
 	if (e == cudaSuccess)
 		e = cudaMemcpyAsync(d_lines, lines.data(), lines.size(),
 		    cudaMemcpyHostToDevice, s->stream);
@@ -224,9 +309,9 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 		    s->stream);
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(s->stream);
-	cudaFree(d_lines);
-	cudaFree(d_offs);
-	cudaFree(d_res);
+	cached_free(d_lines);
+	cached_free(d_offs);
+	cached_free(d_res);
 	if (e != cudaSuccess)
 		return s->cuda(e, "template resolve");
 	std::vector<u8> blob;
@@ -236,7 +321,7 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 		return 0;
 	size_t padded = (blob.size() + 127) & ~(size_t)127;
 	blob.resize(padded, 0);
-	CK(s, cudaMalloc(&s->d_tmpl, padded));
+	CK(s, DEV_ALLOC(s, &s->d_tmpl, padded));
 	CK(s, cudaMemcpyAsync(s->d_tmpl, blob.data(), padded,
 	    cudaMemcpyHostToDevice, s->stream));
 	CK(s, cudaStreamSynchronize(s->stream));
@@ -433,10 +518,23 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 	do {
 		if ((rc = s->cuda(cudaSetDevice(device), "cudaSetDevice")))
 			break;
+		/* cudaGetDeviceProperties costs about a millisecond: once
+		 * per device */
+		static std::mutex prop_mu;
+		static std::map<int, cudaDeviceProp> props;
 		cudaDeviceProp prop;
-		if ((rc = s->cuda(cudaGetDeviceProperties(&prop, device),
-		    "cudaGetDeviceProperties")))
-			break;
+		{
+			std::lock_guard<std::mutex> g(prop_mu);
+			auto it = props.find(device);
+			if (it == props.end()) {
+				if ((rc = s->cuda(cudaGetDeviceProperties(&prop,
+				    device), "cudaGetDeviceProperties")))
+					break;
+				props[device] = prop;
+			} else {
+				prop = it->second;
+			}
+		}
 		s->sm_count = prop.multiProcessorCount;
 		if (const char *ev = getenv("DNG_TEMPLATES"))
 			s->tmpl_enabled = atoi(ev) != 0;
@@ -517,11 +615,13 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		if ((rc = s->cuda(cudaStreamCreateWithFlags(&s->copy_stream,
 		    cudaStreamNonBlocking), "cudaStreamCreate")))
 			break;
-		if ((rc = s->cuda(cudaMalloc(&s->d_plan, sizeof (DevPlan) + 256),
+		if ((rc = s->cuda(DEV_ALLOC(s, &s->d_plan, sizeof (DevPlan) + 256),
 		    "cudaMalloc plan")))
 			break;
-		if ((rc = s->cuda(cudaMemcpy(s->d_plan, &plan->dev,
-		    sizeof (DevPlan), cudaMemcpyHostToDevice), "plan upload")))
+		/* s->plan is this scan's own copy: safe to upload from */
+		if ((rc = s->cuda(cudaMemcpyAsync(s->d_plan, &s->plan.dev,
+		    sizeof (DevPlan), cudaMemcpyHostToDevice, s->stream),
+		    "plan upload")))
 			break;
 		size_t cap = env_size("DNG_TABLE_CAP", (size_t)1 << 20);
 		size_t c2 = 1024;
@@ -529,32 +629,37 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 			c2 <<= 1;
 		s->table_cap = c2;
 		size_t arena = env_size("DNG_ARENA_BYTES", (size_t)64 << 20);
-		if ((rc = s->cuda(cudaMalloc(&s->tab.entries,
+		if ((rc = s->cuda(DEV_ALLOC(s, &s->tab.entries,
 		    c2 * sizeof (GEntry)), "cudaMalloc table")))
 			break;
-		if ((rc = s->cuda(cudaMalloc(&s->tab.arena, arena),
+		if ((rc = s->cuda(DEV_ALLOC(s, &s->tab.arena, arena),
 		    "cudaMalloc arena")))
 			break;
-		if ((rc = s->cuda(cudaMalloc(&s->tab.misc, 16 * sizeof (u32)),
+		if ((rc = s->cuda(DEV_ALLOC(s, &s->tab.misc, 16 * sizeof (u32)),
 		    "cudaMalloc misc")))
 			break;
 		s->tab.mask = (u32)(c2 - 1);
 		s->tab.arena_cap = (u32)arena;
-		cudaMemset(s->tab.entries, 0, c2 * sizeof (GEntry));
-		cudaMemset(s->tab.misc, 0, 16 * sizeof (u32));
+		cudaMemsetAsync(s->tab.entries, 0, c2 * sizeof (GEntry), s->stream);
+		cudaMemsetAsync(s->tab.misc, 0, 16 * sizeof (u32), s->stream);
 		const size_t nctr = NCTR + (MAX_METRICS - 1) * MCTR_PER;
-		if ((rc = s->cuda(cudaMalloc(&s->d_counters,
+		if ((rc = s->cuda(DEV_ALLOC(s, &s->d_counters,
 		    nctr * sizeof (unsigned long long)), "cudaMalloc counters")))
 			break;
-		cudaMemset(s->d_counters, 0, nctr * sizeof (unsigned long long));
-		if ((rc = s->cuda(cudaMalloc(&s->d_nl,
+		cudaMemsetAsync(s->d_counters, 0,
+		    nctr * sizeof (unsigned long long), s->stream);
+		if ((rc = s->cuda(DEV_ALLOC(s, &s->d_nl,
 		    2 * sizeof (unsigned long long)), "cudaMalloc nl")))
 			break;
-		if ((rc = s->cuda(cudaMalloc(&s->d_carry, CARRY_ROOM + 64),
+		if ((rc = s->cuda(DEV_ALLOC(s, &s->d_carry, CARRY_ROOM + 64),
 		    "cudaMalloc carry")))
 			break;
 		s->ring_cap = env_size("DNG_RING_BYTES", (size_t)64 << 20);
-		rc = s->cuda(cudaDeviceSynchronize(), "init");
+		/* whichever stream the scan ends up on waits for this setup */
+		if ((rc = s->cuda(cudaEventCreateWithFlags(&s->ev_init,
+		    cudaEventDisableTiming), "cudaEventCreate")))
+			break;
+		rc = s->cuda(cudaEventRecord(s->ev_init, s->stream), "init");
 	} while (0);
 	if (rc) {
 		set_err(err, errlen, "%s", s->err.c_str());
@@ -573,6 +678,7 @@ int dng_scan_set_stream(dng_scan *s, void *cuda_stream)
 	if (s->launches || s->bytes_fed)
 		return s->fail(DNG_EINVAL, "dng_scan_set_stream after a feed");
 	s->stream = (cudaStream_t)cuda_stream;
+	CK(s, cudaStreamWaitEvent(s->stream, s->ev_init, 0));
 	return DNG_OK;
 }
 
@@ -580,7 +686,7 @@ static int ensure_ring(dng_scan *s, bool need_stage)
 {
 	for (size_t i = 0; i < RING_SLOTS; i++) {
 		if (!s->d_ring[i]) {
-			CK(s, cudaMalloc(&s->d_ring[i], CARRY_ROOM +
+			CK(s, DEV_ALLOC(s, &s->d_ring[i], CARRY_ROOM +
 			    s->ring_cap + 64));
 			CK(s, cudaEventCreateWithFlags(&s->ev_ready[i],
 			    cudaEventDisableTiming));
@@ -588,7 +694,7 @@ static int ensure_ring(dng_scan *s, bool need_stage)
 			    cudaEventDisableTiming));
 		}
 		if (need_stage && !s->h_stage[i])
-			CK(s, cudaMallocHost(&s->h_stage[i], s->ring_cap));
+			CK(s, HOST_ALLOC(&s->h_stage[i], s->ring_cap));
 	}
 	return 0;
 }
@@ -677,7 +783,7 @@ static int feed_file_parallel(dng_scan *s, int fd, size_t size, const char *path
 	const size_t LAG = 6;		/* blocks kept back for in-flight DMA */
 	const size_t GROUP = 4;		/* ready neighbours fed as one chunk */
 	if (!s->file_buf) {
-		CK(s, cudaMallocHost(&s->file_buf, NSLOT * BLK));
+		CK(s, HOST_ALLOC(&s->file_buf, NSLOT * BLK));
 		for (size_t i = 0; i < NSLOT; i++)
 			CK(s, cudaEventCreateWithFlags(&s->file_done[i],
 			    cudaEventDisableTiming));
@@ -875,7 +981,7 @@ int dng_scan_feed_device(dng_scan *s, const void *devbuf, size_t len)
 		if (s->carry_len + head > DNG_MAXREC)
 			return s->fail(DNG_ELIMIT, "input line longer than 16 MiB");
 		if (!s->d_side)
-			CK(s, cudaMalloc(&s->d_side, CARRY_ROOM + 64));
+			CK(s, DEV_ALLOC(s, &s->d_side, CARRY_ROOM + 64));
 		CK(s, cudaMemcpyAsync(s->d_side, s->d_carry, s->carry_len,
 		    cudaMemcpyDeviceToDevice, s->stream));
 		CK(s, cudaMemcpyAsync(s->d_side + s->carry_len, d, head,
@@ -1049,8 +1155,11 @@ int dng_scan_finish(dng_scan *s, dng_result **out)
 	if (n) {
 		OutEntry *d_out = nullptr;
 		u32 *d_n = nullptr;
-		CK(s, cudaMalloc(&d_out, (size_t)n * sizeof (OutEntry)));
-		CK(s, cudaMalloc(&d_n, sizeof (u32)));
+		size_t cap_out = 4096;		/* few sizes: cache-friendly */
+		while (cap_out < n)
+			cap_out <<= 1;
+		CK(s, DEV_ALLOC(s, &d_out, cap_out * sizeof (OutEntry)));
+		CK(s, DEV_ALLOC(s, &d_n, 16));
 		CK(s, cudaMemsetAsync(d_n, 0, sizeof (u32), s->stream));
 		compact_kernel<<<256, 256, 0, s->stream>>>(s->tab.entries,
 		    s->tab.mask + 1, d_out, d_n);
@@ -1063,8 +1172,8 @@ int dng_scan_finish(dng_scan *s, dng_result **out)
 			CK(s, cudaMemcpyAsync(arena.data(), s->tab.arena, misc[0],
 			    cudaMemcpyDeviceToHost, s->stream));
 		CK(s, cudaStreamSynchronize(s->stream));
-		cudaFree(d_out);
-		cudaFree(d_n);
+		cached_free(d_out);
+		cached_free(d_n);
 		r->keys.reserve(n);
 		r->values.reserve(n);
 		for (u32 i = 0; i < n; i++) {
@@ -1129,38 +1238,64 @@ int dng_scan_kernel_stats(dng_scan *s, double *kernel_ms, uint64_t *launches,
 	return DNG_OK;
 }
 
+void dng_release_cached(void)
+{
+	BufCache &c = buf_cache();
+	std::multimap<std::pair<int, size_t>, void *> idle;
+	{
+		std::lock_guard<std::mutex> g(c.mu);
+		idle.swap(c.idle);
+		c.idle_dev = c.idle_host = 0;
+	}
+	for (auto &kv : idle) {
+		if (kv.first.first < 0) {
+			cudaFreeHost(kv.second);
+		} else {
+			cudaSetDevice(kv.first.first);
+			cudaFree(kv.second);
+		}
+	}
+}
+
 void dng_scan_destroy(dng_scan *s)
 {
 	if (!s)
 		return;
 	cudaSetDevice(s->device);
-	cudaDeviceSynchronize();
+	if (s->stream)
+		cudaStreamSynchronize(s->stream);
+	if (s->own_stream && s->own_stream != s->stream)
+		cudaStreamSynchronize(s->own_stream);
+	if (s->copy_stream)
+		cudaStreamSynchronize(s->copy_stream);
 	drain_events(s);
+	if (s->ev_init)
+		cudaEventDestroy(s->ev_init);
 	for (auto e : s->ev_pool)
 		cudaEventDestroy(e);
 	for (size_t i = 0; i < RING_SLOTS; i++) {
 		if (s->d_ring[i]) {
-			cudaFree(s->d_ring[i]);
+			cached_free(s->d_ring[i]);
 			cudaEventDestroy(s->ev_ready[i]);
 			cudaEventDestroy(s->ev_free[i]);
 		}
 		if (s->h_stage[i])
-			cudaFreeHost(s->h_stage[i]);
+			cached_free(s->h_stage[i]);
 	}
 	if (s->file_buf) {
-		cudaFreeHost(s->file_buf);
+		cached_free(s->file_buf);
 		for (int i = 0; i < 32; i++)
 			cudaEventDestroy(s->file_done[i]);
 	}
-	cudaFree(s->d_plan);
-	cudaFree(s->d_tmpl);
-	cudaFree(s->tab.entries);
-	cudaFree(s->tab.arena);
-	cudaFree(s->tab.misc);
-	cudaFree(s->d_counters);
-	cudaFree(s->d_nl);
-	cudaFree(s->d_carry);
-	cudaFree(s->d_side);
+	cached_free(s->d_plan);
+	cached_free(s->d_tmpl);
+	cached_free(s->tab.entries);
+	cached_free(s->tab.arena);
+	cached_free(s->tab.misc);
+	cached_free(s->d_counters);
+	cached_free(s->d_nl);
+	cached_free(s->d_carry);
+	cached_free(s->d_side);
 	if (s->own_stream)
 		cudaStreamDestroy(s->own_stream);
 	if (s->copy_stream)

@@ -1076,10 +1076,10 @@ scan_kernel(const ScanArgs a)
  */
 #define DNG_W_SLICE 208				/* bytes per lane: 13 x 16 */
 #define DNG_W_CHUNK (32 * DNG_W_SLICE)		/* 6656 bytes owned per step */
-#define DNG_W_PRELAP 1024
+#define DNG_W_PRELAP 768
 #define DNG_W_SLACK 64
-#define DNG_W_NLCAP 64				/* newline positions per pass */
-#define DNG_W_MAXLINE 768
+#define DNG_W_NLCAP 32				/* newline positions per pass */
+#define DNG_W_MAXLINE 512
 #define DNG_NW (DNG_NT / 32)
 
 static constexpr size_t SMEM_W_BUF = DNG_W_PRELAP + DNG_W_CHUNK + DNG_W_SLACK;

@@ -19,10 +19,16 @@ static inline bool is_ws(u8 c)
 	return c == ' ' || c == '\t' || c == '\r' || c == '\n';
 }
 
-bool tmpl_skeletonize(const u8 *s, u32 n, std::vector<TSeg> &out)
+/*
+ * The lexical walk, reporting literal runs and wildcards to a sink:
+ *   sink.lit(ptr, len)              a literal run
+ *   sink.wild(kind, off, len)       the wildcard that follows it
+ */
+template <class Sink>
+static bool skeleton_walk(const u8 *s, u32 n, Sink &sink)
 {
-	out.clear();
-	std::string stack;		/* '{' or '[' per open container */
+	char stack[64];			/* '{' or '[' per open container */
+	u32 depth = 0;
 	bool expect_key = false;
 	u32 i = 0, lit_start = 0;
 	while (i < n) {
@@ -36,33 +42,29 @@ bool tmpl_skeletonize(const u8 *s, u32 n, std::vector<TSeg> &out)
 			}
 			if (j >= n)
 				return false;
-			if (!stack.empty() && stack.back() == '{' && expect_key) {
+			if (depth && stack[depth - 1] == '{' && expect_key) {
 				expect_key = false;
 				i = j + 1;
 				continue;
 			}
-			TSeg g;
-			g.lit.assign((const char *)s + lit_start, i + 1 - lit_start);
-			g.kind = TK_STR;
-			g.woff = i + 1;
-			g.wlen = j - (i + 1);
-			out.push_back(g);
+			sink.lit(s + lit_start, i + 1 - lit_start);
+			sink.wild(TK_STR, i + 1, j - (i + 1));
 			lit_start = j;
 			i = j + 1;
 		} else if (c == '{' || c == '[') {
-			if (stack.size() >= 64)
+			if (depth >= sizeof (stack))
 				return false;
-			stack.push_back((char)c);
+			stack[depth++] = (char)c;
 			expect_key = c == '{';
 			i++;
 		} else if (c == '}' || c == ']') {
-			if (stack.empty() || stack.back() != (c == '}' ? '{' : '['))
+			if (!depth || stack[depth - 1] != (c == '}' ? '{' : '['))
 				return false;
-			stack.pop_back();
+			depth--;
 			expect_key = false;
 			i++;
 		} else if (c == ',') {
-			expect_key = !stack.empty() && stack.back() == '{';
+			expect_key = depth && stack[depth - 1] == '{';
 			i++;
 		} else if (c == ':' || is_ws(c)) {
 			i++;
@@ -71,33 +73,57 @@ bool tmpl_skeletonize(const u8 *s, u32 n, std::vector<TSeg> &out)
 			while (j < n && s[j] != ',' && s[j] != ']' && s[j] != '}' &&
 			    s[j] != ':' && s[j] != '"' && !is_ws(s[j]))
 				j++;
-			TSeg g;
-			g.lit.assign((const char *)s + lit_start, i - lit_start);
-			g.kind = TK_BARE;
-			g.woff = i;
-			g.wlen = j - i;
-			out.push_back(g);
+			sink.lit(s + lit_start, i - lit_start);
+			sink.wild(TK_BARE, i, j - i);
 			lit_start = j;
 			i = j;
 		}
 	}
-	if (!stack.empty())
+	if (depth)
 		return false;
-	TSeg g;
-	g.lit.assign((const char *)s + lit_start, n - lit_start);
-	g.kind = TK_NONE;
-	g.woff = n;
-	g.wlen = 0;
-	out.push_back(g);
+	sink.lit(s + lit_start, n - lit_start);
+	sink.wild(TK_NONE, n, 0);
 	return true;
+}
+
+namespace {
+struct SegSink {
+	std::vector<TSeg> &out;
+	TSeg cur;
+	void lit(const u8 *p, u32 n) { cur.lit.assign((const char *)p, n); }
+	void wild(u8 kind, u32 off, u32 len) {
+		cur.kind = kind;
+		cur.woff = off;
+		cur.wlen = len;
+		out.push_back(cur);
+	}
+};
+struct HashSink {		/* FNV-1a over literals and wildcard kinds */
+	u64 h = 1469598103934665603ull;
+	void lit(const u8 *p, u32 n) {
+		for (u32 i = 0; i < n; i++)
+			h = (h ^ p[i]) * 1099511628211ull;
+	}
+	void wild(u8 kind, u32, u32) {
+		h = (h ^ (0x100u + kind)) * 1099511628211ull;
+	}
+};
+}
+
+bool tmpl_skeletonize(const u8 *s, u32 n, std::vector<TSeg> &out)
+{
+	out.clear();
+	SegSink sink{out, TSeg()};
+	return skeleton_walk(s, n, sink);
 }
 
 void tmpl_candidates(const u8 *data, size_t len, size_t maxk,
     std::vector<TCandidate> &out)
 {
 	out.clear();
-	std::map<std::string, size_t> seen;
-	std::vector<TSeg> segs;
+	/* count shapes by a hash of their skeleton; only the first line of each
+	 * distinct shape is broken into segments */
+	std::map<u64, size_t> seen;
 	size_t pos = 0, nlines = 0;
 	while (pos < len && nlines < 8192) {
 		const u8 *nl = (const u8 *)memchr(data + pos, '\n', len - pos);
@@ -109,24 +135,20 @@ void tmpl_candidates(const u8 *data, size_t len, size_t maxk,
 		nlines++;
 		if (n == 0 || n > TMPL_MAX_LINE)
 			continue;
-		if (!tmpl_skeletonize(line, (u32)n, segs))
+		HashSink hs;
+		if (!skeleton_walk(line, (u32)n, hs))
 			continue;
-		std::string key;
-		for (const TSeg &g : segs) {
-			key += g.lit;
-			key.push_back((char)(1 + g.kind));
-		}
-		auto it = seen.find(key);
+		auto it = seen.find(hs.h);
 		if (it != seen.end()) {
 			out[it->second].count++;
 			continue;
 		}
 		if (seen.size() >= 256)
 			continue;
-		seen[key] = out.size();
+		seen[hs.h] = out.size();
 		TCandidate c;
 		c.sample.assign((const char *)line, n);
-		c.segs = segs;
+		tmpl_skeletonize(line, (u32)n, c.segs);
 		c.count = 1;
 		out.push_back(c);
 	}

@@ -69,6 +69,7 @@ _SIGS = [
      [_P, ctypes.c_int, ctypes.POINTER(DngCounters)]),
     ('dng_scan_error', ctypes.c_char_p, [_P]),
     ('dng_scan_destroy', None, [_P]),
+    ('dng_release_cached', None, []),
     ('dng_scan_kernel_stats', ctypes.c_int,
      [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64),
       ctypes.POINTER(ctypes.c_uint64)]),

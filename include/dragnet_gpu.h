@@ -136,6 +136,10 @@ int dng_scan_counters(dng_scan *scan, dng_counters *out);
 int dng_scan_counters_metric(dng_scan *scan, int metric, dng_counters *out);
 const char *dng_scan_error(const dng_scan *scan);
 void dng_scan_destroy(dng_scan *scan);
+/* Destroyed scans keep their device and pinned buffers for the next scan of
+ * this process (bounded by DNG_CACHE_BYTES per kind, default 2 GiB); this
+ * returns them to the driver. */
+void dng_release_cached(void);
 
 /* Device time (ms, CUDA events on the scan stream) spent in scan kernels and
  * the number of kernel launches since open; for bench.py's roofline. */

@@ -23,7 +23,7 @@ for cub in glob.glob(os.path.join(d, 'api*.cubin')):
         if m:
             fl, ln = m.group(1).split('/')[-1], int(m.group(2))
         m = re.match(r'^\s*/\*([0-9a-f]{4,})\*/\s+(\S.*?);', l)
-        if m and fn and 'scan_kernel' in fn and 'ScanArgs' in fn:
+        if m and fn and (os.environ.get('NCU_FN', 'scan_kernel_w') + 'ENS_8ScanArgs') in fn:
             addr2line[int(m.group(1), 16)] = (fl, ln)
 skip = os.environ.get('NCU_SKIP', '0')
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv',
