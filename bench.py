@@ -313,6 +313,7 @@ def gpu_arm(args, rank, local_rank, world):
         e1.record()
         e1.synchronize()
         st = s.kernel_stats()
+        st.update(s.template_stats())
         ms = e0.elapsed_time(e1)
         s.close()
         return pts, counters, st, ms
@@ -486,12 +487,18 @@ def gpu_arm(args, rank, local_rank, world):
             'l2': 'inputs (%.1f GB) >> L2 (126 MB): no flush needed' %
                   (nbytes / 1e9),
             'points': len(R['last'][0]) if R['last'][0] is not None else None,
+            # what the scan specialised itself to from the head of the input
+            'kernel': R['last'][2]['kernel'],
+            'record_templates': R['last'][2]['templates'],
+            'templated_fraction': R['last'][2]['templated_records'] /
+            max(1, R['last'][1]['lines']),
         },
         'roofline': {
             'bound': 'hbm', 'achieved': achieved, 'peak': peak,
             'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
             'traffic_source': traffic_src,
-            'kernel': 'dng::scan_kernel',
+            'kernel': 'dng::scan_kernel_w' if R['last'][2]['kernel'] ==
+            'per-warp chunks' else 'dng::scan_kernel',
             'bytes_per_launch': R['kernel_bytes'] / n_launch,
             'ms_per_launch': R['kernel_ms'] / n_launch,
             'peak_source': '%s HBM copy bandwidth (MEASURED_PEAKS.json)' % how,

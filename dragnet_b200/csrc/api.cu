@@ -1221,6 +1221,13 @@ int dng_scan_template_stats(dng_scan *s, uint64_t *templates,
 	return DNG_OK;
 }
 
+int dng_scan_kernel_kind(const dng_scan *s)
+{
+	if (!s)
+		return DNG_EINVAL;
+	return s->warp_kernel ? 1 : 0;
+}
+
 int dng_scan_kernel_stats(dng_scan *s, double *kernel_ms, uint64_t *launches,
     uint64_t *kernel_bytes)
 {

@@ -76,6 +76,7 @@ _SIGS = [
     ('dng_scan_set_templates', ctypes.c_int, [_P, ctypes.c_int]),
     ('dng_scan_template_stats', ctypes.c_int,
      [_P, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    ('dng_scan_kernel_kind', ctypes.c_int, [_P]),
     ('dng_pinned_alloc', _P, [ctypes.c_size_t]),
     ('dng_pinned_free', None, [_P]),
     ('dng_result_count', ctypes.c_size_t, [_P]),
@@ -346,7 +347,10 @@ class Scan(object):
         r = ctypes.c_uint64()
         _check(lib().dng_scan_template_stats(self.handle, ctypes.byref(t),
                                              ctypes.byref(r)), self.handle)
-        return {'templates': int(t.value), 'templated_records': int(r.value)}
+        return {'templates': int(t.value), 'templated_records': int(r.value),
+                'kernel': 'per-warp chunks'
+                if lib().dng_scan_kernel_kind(self.handle) == 1
+                else 'CTA tiles'}
 
     def close(self):
         if self.handle:

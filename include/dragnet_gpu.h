@@ -158,6 +158,13 @@ int dng_scan_set_templates(dng_scan *scan, int enable);
 int dng_scan_template_stats(dng_scan *scan, uint64_t *templates,
     uint64_t *templated_records);
 
+/*
+ * Which kernel geometry the scan runs (chosen from the sampled line lengths
+ * at the first feed; environment DNG_KERNEL=tile|warp forces one): 0 = CTA-wide
+ * tiles (any line length), 1 = per-warp chunks (short lines).
+ */
+int dng_scan_kernel_kind(const dng_scan *scan);
+
 void *dng_pinned_alloc(size_t len);
 void dng_pinned_free(void *p);
 
