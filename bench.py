@@ -491,7 +491,7 @@ def gpu_arm(args, rank, local_rank, world):
             'kernel': R['last'][2]['kernel'],
             'record_templates': R['last'][2]['templates'],
             'templated_fraction': R['last'][2]['templated_records'] /
-            max(1, R['last'][1]['lines']),
+            max(1, R['last'][1]['lines'] / world),
         },
         'roofline': {
             'bound': 'hbm', 'achieved': achieved, 'peak': peak,

@@ -165,6 +165,7 @@ struct dng_scan {
 	bool tmpl_enabled = true, tmpl_tried = false;
 	/* kernel geometry: per-warp chunks for short lines, CTA tiles otherwise */
 	bool warp_kernel = false;
+	u32 wslice = DNG_W_SLICE_MAX;	/* bytes per lane of a warp's chunk */
 	int kernel_pref = 0;		/* DNG_KERNEL: 0 auto, 1 tile, 2 warp */
 	u32 w_sslots = 0, w_s1slots = 0;
 	u8 *d_tmpl = nullptr;
@@ -262,6 +263,24 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 		longest = std::max(longest, run);
 		s->warp_kernel = longest <= DNG_W_MAXLINE;
 	}
+	{
+		/* chunk size: the lane slice (16 x odd bytes) whose chunk holds
+		 * the most records per 32-lane pass, given the mean line */
+		size_t nl = 0;
+		for (size_t i = 0; i < n; i++)
+			nl += head[i] == '\n';
+		double mean = nl ? (double)n / (double)nl : 224.0;
+		double best = -1;
+		for (u32 sl = 112; sl <= DNG_W_SLICE_MAX; sl += 32) {
+			double recs = 32.0 * sl / mean;
+			double passes = ceil((recs + 1.5) / 32.0);
+			double util = recs / (32.0 * passes);
+			if (util >= best) {
+				best = util;
+				s->wslice = sl;
+			}
+		}
+	}
 	if (!s->tmpl_enabled)
 		return 0;
 	std::vector<TCandidate> cands;
@@ -349,9 +368,12 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 	a.plan_bytes = s->plan_bytes;
 	a.tmpl = s->d_tmpl;
 	a.tmpl_bytes = s->tmpl_bytes;
+	a.wslice = DNG_W_SLICE_MAX;
 	cudaEvent_t e0 = get_event(s), e1 = get_event(s);
 	if (s->warp_kernel) {
-		a.ntiles = (u32)((nbytes + DNG_W_CHUNK - 1) / DNG_W_CHUNK);
+		const unsigned long long chunk = 32ull * s->wslice;
+		a.wslice = s->wslice;
+		a.ntiles = (u32)((nbytes + chunk - 1) / chunk);
 		a.sslots = s->w_sslots;
 		a.s1slots = s->w_s1slots;
 		u32 grid = std::min<u32>((a.ntiles + DNG_NW - 1) / DNG_NW,

@@ -116,6 +116,7 @@ struct ScanArgs {
 	u32 plan_bytes;			/* devplan_smem_bytes(plan) */
 	u32 sslots;			/* tier-2 slots (power of two) */
 	u32 s1slots;			/* tier-1 slots (power of two) */
+	u32 wslice;			/* per-warp kernel: bytes per lane (16 x odd) */
 	const u8 *tmpl;			/* record templates (tmpl.h blob) or null */
 	u32 tmpl_bytes;			/* multiple of 128, 0 = no templates */
 };
@@ -1074,8 +1075,11 @@ scan_kernel(const ScanArgs a)
  * the HBM path, so the host picks this kernel only for input whose (sampled)
  * lines are short (DNG_W_MAXLINE) and the CTA-wide kernel otherwise.
  */
-#define DNG_W_SLICE 208				/* bytes per lane: 13 x 16 */
-#define DNG_W_CHUNK (32 * DNG_W_SLICE)		/* 6656 bytes owned per step */
+/* a chunk is 32 lane slices of a.wslice bytes (16 x an odd number, so that the
+ * lanes' uint4 reads do not collide on banks); the host picks the slice that
+ * puts just under 32 (or 64, ...) average records in a chunk */
+#define DNG_W_SLICE_MAX 208			/* 13 x 16 */
+#define DNG_W_CHUNK (32 * DNG_W_SLICE_MAX)	/* largest chunk: 6656 bytes */
 #define DNG_W_PRELAP 768
 #define DNG_W_SLACK 64
 #define DNG_W_NLCAP 32				/* newline positions per pass */
@@ -1158,11 +1162,12 @@ scan_kernel_w(const ScanArgs a)
 	const u32 ltmask = (1u << lane) - 1;
 
 	const u32 nwarps = gridDim.x * DNG_NW;
+	const u32 chunk = 32 * a.wslice;
 	for (u32 ch = blockIdx.x * DNG_NW + wid; ch < a.ntiles; ch += nwarps) {
-		const unsigned long long g0 = (unsigned long long)ch * DNG_W_CHUNK;
+		const unsigned long long g0 = (unsigned long long)ch * chunk;
 		const unsigned long long ws = g0 >= DNG_W_PRELAP ?
 		    g0 - DNG_W_PRELAP : 0;
-		unsigned long long we = g0 + DNG_W_CHUNK;
+		unsigned long long we = g0 + chunk;
 		if (we > a.nbytes)
 			we = a.nbytes;
 		const u32 wlen = (u32)(we - ws);
@@ -1176,11 +1181,11 @@ scan_kernel_w(const ScanArgs a)
 			tma_load_1d(sdata, a.data + ws, bulk, mbar);
 			/* start pulling this warp's next chunk into L2 */
 			unsigned long long nx = g0 +
-			    (unsigned long long)nwarps * DNG_W_CHUNK;
-			if (nx + DNG_W_CHUNK <= a.nbytes)
+			    (unsigned long long)nwarps * chunk;
+			if (nx + chunk <= a.nbytes)
 				asm volatile("cp.async.bulk.prefetch.L2.global "
 				    "[%0], %1;" :: "l"(a.data + nx),
-				    "r"((u32)DNG_W_CHUNK) : "memory");
+				    "r"(chunk) : "memory");
 		}
 		for (u32 i = bulk + lane; i < wlen; i += 32)
 			sdata[i] = a.data[ws + i];
@@ -1196,7 +1201,7 @@ scan_kernel_w(const ScanArgs a)
 		w.wlen = wlen;
 		w.lower = lower;
 		/* this lane's slice of the chunk, 16-byte words */
-		u32 c0 = off0 + lane * DNG_W_SLICE, c1 = c0 + DNG_W_SLICE;
+		u32 c0 = off0 + lane * a.wslice, c1 = c0 + a.wslice;
 		if (c1 > wlen)
 			c1 = wlen;
 		u32 cnt = 0;

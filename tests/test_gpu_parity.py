@@ -285,3 +285,26 @@ def test_scalar_forms_behind_one_template(tmp_path):
         assert canon_points(r.points) == canon_points(exp_p), argv
         assert r.counters == exp_c, argv
         assert r.stats['templated_records'] > 20, r.stats
+
+
+@pytest.mark.parametrize('pad', [0, 40, 90, 140, 260, 380, 700])
+def test_line_lengths_pick_different_chunk_geometries(pad, tmp_path):
+    """The per-warp kernel sizes its chunks from the sampled mean line length
+    (and gives way to the tile kernel for long lines): same answers at every
+    size."""
+    import random
+    rng = random.Random(pad)
+    lines = []
+    for i in range(30000):
+        extra = b'y' * rng.randrange(0, 9)
+        lines.append(b'{"a":"k%d","n":%d,"pad":"' % (i % 11, i % 97) +
+                     b'x' * pad + extra + b'","b":{"c":%s}}' %
+                     (b'null' if i % 5 == 0 else b'"v%d"' % (i % 3)))
+    lines[777] = lines[777][:-1]                    # invalid
+    path = _write(tmp_path, 'len.log', lines)
+    for argv in (['-b', 'a,b.c'], ['-b', 'n[aggr=lquantize,step=10]']):
+        plan = corpus.make_plan(argv)
+        exp_p, exp_c = py_engine(plan, [path])
+        act_p, act_c = gpu_engine(plan, [path])
+        assert canon_points(act_p) == canon_points(exp_p), (pad, argv)
+        assert act_c == exp_c, (pad, argv)
