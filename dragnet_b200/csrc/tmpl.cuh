@@ -10,7 +10,8 @@
  * instead, so this function only ever has to be right when it says yes.
  *
  * The values it stores are exactly what fast_finish() (record.cuh) makes of
- * the automaton's captures: strings without escapes as (T_STR, body span),
+ * the automaton's captures: strings as (T_STR, body span, VF_ESCAPED if the
+ * body holds a backslash),
  * numbers with VF_SIMPLEINT decided by the same rule, containers as
  * (T_OBJ|T_ARR, start).
  *
@@ -100,22 +101,49 @@ DNG_HD bool tmpl_match(M &m, u32 len, RecState &R, bool active)
 		u64 val = 0;
 		const u32 kind = nd.z & 0xff;
 		if (ok && kind == TK_STR) {
-			/* first '"', '\\' or control byte from q on */
-			typename M::Cur c = m.cursor(q);
-			u32 e = q, hit, w;
+			/* first '"', '\\' or control byte from q on; an escape
+			 * is checked and stepped over, and the scan goes on */
+			u32 e = q, esc = 0;
 			for (;;) {
-				w = c.next();
-				hit = tz_low(w ^ 0x22222222u) |
-				    tz_low(w ^ 0x5c5c5c5cu) |
-				    tz_low(w & 0xe0e0e0e0u);
-				if (hit)
+				typename M::Cur c = m.cursor(e);
+				u32 hit, w;
+#pragma unroll 2
+				for (;;) {
+					w = c.next();
+					hit = tz_low(w ^ 0x22222222u) |
+					    tz_low(w ^ 0x5c5c5c5cu) |
+					    tz_low(w & 0xe0e0e0e0u);
+					if (hit)
+						break;
+					e += 4;
+				}
+				const u32 b = low_flag_byte(hit);
+				e += b;
+				const u32 stop = (w >> (8 * b)) & 0xff;
+				if (stop != '\\') {
+					ok = stop == '"';
 					break;
-				e += 4;
+				}
+				/* \" \\ \/ \b \f \n \r \t \uXXXX (what JSON.parse
+				 * accepts); the record's '\n' ends a truncated one */
+				const u32 c1 = m.byte(e + 1);
+				if (c1 == 'u') {
+					ok = is_hex(m.byte(e + 2)) &&
+					    is_hex(m.byte(e + 3)) &&
+					    is_hex(m.byte(e + 4)) &&
+					    is_hex(m.byte(e + 5));
+					e += 6;
+				} else {
+					ok = c1 == '"' || c1 == '\\' || c1 == '/' ||
+					    c1 == 'b' || c1 == 'f' || c1 == 'n' ||
+					    c1 == 'r' || c1 == 't';
+					e += 2;
+				}
+				esc = VF_ESCAPED;
+				if (!ok)
+					break;
 			}
-			const u32 b = low_flag_byte(hit);
-			e += b;
-			ok = ((w >> (8 * b)) & 0xff) == '"';
-			val = mkval(T_STR, q, e - q, 0);
+			val = mkval(T_STR, q, e - q, esc);
 			q = e;
 		} else if (ok && kind == TK_BARE) {
 			typename M::Cur c = m.cursor(q);
