@@ -168,6 +168,12 @@ struct dng_scan {
 	u32 wslice = DNG_W_SLICE_MAX;	/* bytes per lane of a warp's chunk */
 	int kernel_pref = 0;		/* DNG_KERNEL: 0 auto, 1 tile, 2 warp */
 	u32 w_sslots = 0, w_s1slots = 0;
+	/* counters of finished launches, copied to pinned memory after every
+	 * launch: lets the host notice that the input changed character */
+	unsigned long long *h_live = nullptr;
+	unsigned long long learn_lines = 0, learn_tmpl = 0;
+	unsigned long long seen_lines = 0, seen_long = 0;
+	int relearns = 0;
 	u8 *d_tmpl = nullptr;
 	u32 tmpl_bytes = 0, ntemplates = 0;
 	std::string err;
@@ -340,6 +346,10 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 		return 0;
 	size_t padded = (blob.size() + 127) & ~(size_t)127;
 	blob.resize(padded, 0);
+	/* (the stream is idle here: a blob being replaced is not in use) */
+	cached_free(s->d_tmpl);
+	s->d_tmpl = nullptr;
+	s->tmpl_bytes = 0;
 	CK(s, DEV_ALLOC(s, &s->d_tmpl, padded));
 	CK(s, cudaMemcpyAsync(s->d_tmpl, blob.data(), padded,
 	    cudaMemcpyHostToDevice, s->stream));
@@ -355,8 +365,42 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 {
 	if (nbytes <= start)
 		return 0;
-	if (!s->tmpl_tried && learn_templates(s, data, start, nbytes))
-		return s->err_code;
+	if (!s->tmpl_tried) {
+		if (learn_templates(s, data, start, nbytes))
+			return s->err_code;
+	} else if (s->h_live) {
+		/*
+		 * Input that changes character mid-stream (another file,
+		 * another producer): many lines longer than a warp's pre-lap
+		 * -> the tile kernel from here on; most records missing the
+		 * templates -> learn again from this data (a few times at most;
+		 * each costs a stream synchronisation).
+		 */
+		const volatile unsigned long long *lv = s->h_live;
+		const unsigned long long lines = lv[CTR_LINES];
+		const unsigned long long nlong = lv[CTR_LONG];
+		if (lines - s->seen_lines >= 64) {
+			/* over the launches that finished since the last look */
+			if (s->warp_kernel && s->kernel_pref == 0 &&
+			    (nlong - s->seen_long) * 16 > lines - s->seen_lines)
+				s->warp_kernel = false;
+			s->seen_lines = lines;
+			s->seen_long = nlong;
+		}
+		const unsigned long long dl = lines - s->learn_lines;
+		if (s->tmpl_enabled && s->relearns < 3 && dl > 200000 &&
+		    (lv[CTR_TMPL] - s->learn_tmpl) * 2 < dl) {
+			s->relearns++;
+			const bool wk = s->warp_kernel;
+			if (learn_templates(s, data, start, nbytes))
+				return s->err_code;
+			if (!wk && s->kernel_pref == 0)
+				s->warp_kernel = false;	/* long lines were seen */
+			/* the stream is idle: the counters below are current */
+			s->learn_lines = lv[CTR_LINES];
+			s->learn_tmpl = lv[CTR_TMPL];
+		}
+	}
 	ScanArgs a;
 	a.data = data;
 	a.start = start;
@@ -394,6 +438,13 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 		    a.s1slots * sizeof (SSlot1), s->stream>>>(a);
 	}
 	cudaEventRecord(e1, s->stream);
+	if (!s->h_live && HOST_ALLOC(&s->h_live, 16 * sizeof (unsigned long long))
+	    == cudaSuccess)
+		memset(s->h_live, 0, 16 * sizeof (unsigned long long));
+	if (s->h_live)
+		cudaMemcpyAsync(s->h_live, s->d_counters,
+		    16 * sizeof (unsigned long long), cudaMemcpyDeviceToHost,
+		    s->stream);
 	s->ev_pairs.emplace_back(e0, e1);
 	s->launches++;
 	s->kernel_bytes += nbytes - start;
@@ -1316,6 +1367,7 @@ void dng_scan_destroy(dng_scan *s)
 		for (int i = 0; i < 32; i++)
 			cudaEventDestroy(s->file_done[i]);
 	}
+	cached_free(s->h_live);
 	cached_free(s->d_plan);
 	cached_free(s->d_tmpl);
 	cached_free(s->tab.entries);

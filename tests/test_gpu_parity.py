@@ -10,7 +10,7 @@ import pytest
 
 sys.path.insert(0, os.path.dirname(__file__))
 import corpus  # noqa: E402
-from engines import canon_points, py_engine  # noqa: E402
+from engines import canon_points, cpp_engine, py_engine  # noqa: E402
 from golden_harness import check_section  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -308,3 +308,46 @@ def test_line_lengths_pick_different_chunk_geometries(pad, tmp_path):
         act_p, act_c = gpu_engine(plan, [path])
         assert canon_points(act_p) == canon_points(exp_p), (pad, argv)
         assert act_c == exp_c, (pad, argv)
+
+
+def _chunks(data, n):
+    return [data[i:i + n] for i in range(0, len(data), n)]
+
+
+def test_stream_that_changes_shape_is_relearned(tmp_path):
+    """Templates come from the head of the first data; when later input has
+    another shape the scan notices (most records miss) and learns again."""
+    from dragnet_b200 import datasource_gpu
+    a = b''.join(b'{"a":"x%d","n":%d}\n' % (i % 5, i % 13)
+                 for i in range(300000))
+    b = b''.join(b'{"kind":"b","a":"y%d","m":{"z":%d},"n":%d}\n' %
+                 (i % 7, i % 3, i % 17) for i in range(1200000))
+    path = tmp_path / 'two.log'
+    path.write_bytes(a + b)
+    plan = corpus.make_plan(['-b', 'a,n'])
+    exp_p, exp_c = cpp_engine(plan, [str(path)], threads=8)
+    r = datasource_gpu.run_plan(plan, chunks=_chunks(a + b, 4 << 20))
+    assert canon_points(r.points) == canon_points(exp_p)
+    assert r.counters == exp_c
+    if os.environ.get('DNG_KERNEL') != 'tile':
+        # the later shape got its own template for most of its records
+        assert r.stats['templated_records'] > 0.6 * 1500000, r.stats
+
+
+def test_stream_that_turns_to_long_lines_switches_kernel(tmp_path):
+    """Short lines first (per-warp chunks are chosen), then 3 KB lines: they
+    straddle the warps' pre-lap, the scan falls back to CTA-wide tiles."""
+    from dragnet_b200 import datasource_gpu
+    a = b''.join(b'{"a":"x%d","n":%d}\n' % (i % 5, i % 13)
+                 for i in range(300000))
+    b = b''.join(b'{"a":"L%d","pad":"' % (i % 3) + b'p' * 3000 +
+                 b'","n":%d}\n' % (i % 7) for i in range(12000))
+    path = tmp_path / 'long.log'
+    path.write_bytes(a + b)
+    plan = corpus.make_plan(['-b', 'a,n'])
+    exp_p, exp_c = cpp_engine(plan, [str(path)], threads=8)
+    r = datasource_gpu.run_plan(plan, chunks=_chunks(a + b, 4 << 20))
+    assert canon_points(r.points) == canon_points(exp_p)
+    assert r.counters == exp_c
+    if 'DNG_KERNEL' not in os.environ:
+        assert r.stats['kernel'] == 'CTA tiles', r.stats
