@@ -169,6 +169,7 @@ namespace {
 struct PSeg {			/* a template segment with its captures */
 	std::string lit;
 	u8 kind, cap, poscap;
+	u16 posoff;
 };
 
 struct PTmpl {
@@ -190,6 +191,7 @@ bool plan_template(const TCandidate &c, const TResolved &r, PTmpl &t)
 		p.lit = g.lit;
 		p.kind = g.kind;
 		p.cap = p.poscap = 0;
+		p.posoff = 0;
 		t.segs.push_back(p);
 		start.push_back(pos);
 		pos = g.woff + g.wlen;
@@ -197,27 +199,55 @@ bool plan_template(const TCandidate &c, const TResolved &r, PTmpl &t)
 	t.set_mask = r.set_mask;
 	for (int s = 0; s < MAX_SLOTS; s++)
 		t.want[s] = -1;
-	/* first cut the literals so that every captured container opens one */
+	/*
+	 * Captured containers: a literal remembers one (at an offset); a second
+	 * one in the same literal cuts it, so that it opens a literal of its
+	 * own.  In increasing offset order, so that cuts stay behind the
+	 * offsets already recorded.
+	 */
+	std::vector<std::pair<u32, u32>> conts;		/* (offset, slot) */
 	for (u32 s = 0; s < MAX_SLOTS; s++) {
 		if (!((r.set_mask >> s) & 1))
 			continue;
 		u64 v = r.slots[s];
-		u32 type = (u32)(v >> 56) & 0xf, off = (u32)v;
-		if (type != T_OBJ && type != T_ARR)
-			continue;
-		for (size_t i = 0; i < t.segs.size(); i++) {
-			if (off <= start[i] || off >= start[i] + t.segs[i].lit.size())
+		u32 type = (u32)(v >> 56) & 0xf;
+		if (type == T_OBJ || type == T_ARR)
+			conts.push_back(std::make_pair((u32)v, s));
+	}
+	std::sort(conts.begin(), conts.end());
+	for (auto &c2 : conts) {
+		const u32 off = c2.first, slot = c2.second;
+		bool found = false;
+		for (size_t i = 0; i < t.segs.size() && !found; i++) {
+			if (off < start[i] || off >= start[i] + t.segs[i].lit.size())
 				continue;
-			u32 d = off - start[i];
-			PSeg head;
-			head.lit = t.segs[i].lit.substr(0, d);
-			head.kind = TK_NONE;
-			head.cap = head.poscap = 0;
-			t.segs[i].lit.erase(0, d);
-			t.segs.insert(t.segs.begin() + i, head);
-			start.insert(start.begin() + i + 1, off);
-			break;
+			if (t.segs[i].poscap) {
+				u32 d = off - start[i];
+				if (d == 0 || d <= t.segs[i].posoff)
+					return false;
+				PSeg head;
+				head.lit = t.segs[i].lit.substr(0, d);
+				head.kind = TK_NONE;
+				head.cap = 0;
+				head.poscap = t.segs[i].poscap;
+				head.posoff = t.segs[i].posoff;
+				t.segs[i].lit.erase(0, d);
+				t.segs[i].poscap = 0;
+				t.segs.insert(t.segs.begin() + i, head);
+				start.insert(start.begin() + i + 1, off);
+				i++;
+			}
+			char open = t.segs[i].lit[off - start[i]];
+			u32 type = (u32)(r.slots[slot] >> 56) & 0xf;
+			if (open != (type == T_OBJ ? '{' : '['))
+				return false;
+			t.segs[i].poscap = (u8)(slot + 1);
+			t.segs[i].posoff = (u16)(off - start[i]);
+			t.want[slot] = 1;	/* fixed up below */
+			found = true;
 		}
+		if (!found)
+			return false;
 	}
 	for (u32 s = 0; s < MAX_SLOTS; s++) {
 		if (!((r.set_mask >> s) & 1))
@@ -227,29 +257,28 @@ bool plan_template(const TCandidate &c, const TResolved &r, PTmpl &t)
 		u32 off = (u32)v;
 		if (flags & VF_INLINE)
 			return false;
+		if (type == T_OBJ || type == T_ARR)
+			continue;		/* placed above */
 		bool found = false;
 		for (size_t i = 0; i < t.segs.size() && !found; i++) {
 			PSeg &g = t.segs[i];
-			if (type == T_OBJ || type == T_ARR) {
-				if (start[i] != off || g.lit.empty() ||
-				    g.lit[0] != (type == T_OBJ ? '{' : '['))
-					continue;
-				if (g.poscap)
-					return false;
-				g.poscap = (u8)(s + 1);
-			} else {
-				if (g.kind != (type == T_STR ? TK_STR : TK_BARE) ||
-				    start[i] + g.lit.size() != off)
-					continue;
-				if (g.cap)
-					return false;
-				g.cap = (u8)(s + 1);
-			}
-			t.want[s] = (int)i;
+			if (g.kind != (type == T_STR ? TK_STR : TK_BARE) ||
+			    start[i] + g.lit.size() != off)
+				continue;
+			if (g.cap)
+				return false;
+			g.cap = (u8)(s + 1);
 			found = true;
 		}
 		if (!found)
 			return false;
+	}
+	/* which segment supplies each slot (cuts above moved indexes) */
+	for (size_t i = 0; i < t.segs.size(); i++) {
+		if (t.segs[i].poscap)
+			t.want[t.segs[i].poscap - 1] = (int)i;
+		if (t.segs[i].cap)
+			t.want[t.segs[i].cap - 1] = (int)i;
 	}
 	return true;
 }
@@ -257,6 +286,7 @@ bool plan_template(const TCandidate &c, const TResolved &r, PTmpl &t)
 struct BNode {
 	std::string lit;
 	u8 kind, cap, poscap;
+	u16 posoff;
 	std::vector<int> kids;
 	int leaf;
 };
@@ -269,6 +299,7 @@ struct Trie {
 	Trie() : pool(0) {
 		BNode r;
 		r.kind = r.cap = r.poscap = 0;
+		r.posoff = 0;
 		r.leaf = -1;
 		nodes.push_back(r);
 	}
@@ -287,6 +318,7 @@ struct Trie {
 				b.kind = g.kind;
 				b.cap = g.cap;
 				b.poscap = g.poscap;
+				b.posoff = g.posoff;
 				b.leaf = -1;
 				hit = (int)nodes.size();
 				nodes.push_back(b);
@@ -300,9 +332,11 @@ struct Trie {
 					b.cap = g.cap;
 				}
 				if (g.poscap) {
-					if (b.poscap && b.poscap != g.poscap)
+					if (b.poscap && (b.poscap != g.poscap ||
+					    b.posoff != g.posoff))
 						return false;
 					b.poscap = g.poscap;
+					b.posoff = g.posoff;
 				}
 			}
 			cur = hit;
@@ -445,6 +479,7 @@ void tmpl_build(const std::vector<TCandidate> &cands,
 			o.kind = b.kind;
 			o.cap = b.cap;
 			o.poscap = b.poscap;
+			o.posoff = b.posoff;
 			o.alt = j + 1 < kids.size() ? (u16)index[kids[j + 1]] :
 			    (u16)TN_NOALT;
 			o.next = b.leaf >= 0 ? (u16)(TN_LEAF | b.leaf) :

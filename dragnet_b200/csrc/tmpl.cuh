@@ -209,9 +209,11 @@ DNG_HD bool tmpl_match(M &m, u32 len, RecState &R, bool active)
 		} else {
 			const u32 pc = (nd.z >> 16) & 0xff;
 			const u32 cap = (nd.z >> 8) & 0xff;
-			if (pc)
-				R.slots[pc - 1] = mkval(m.byte(p) == '{' ?
-				    T_OBJ : T_ARR, p, 0, 0);
+			if (pc) {
+				const u32 at = p + (nd.w & 0xffff);
+				R.slots[pc - 1] = mkval(m.byte(at) == '{' ?
+				    T_OBJ : T_ARR, at, 0, 0);
+			}
 			if (cap)
 				R.slots[cap - 1] = val;
 			p = q;

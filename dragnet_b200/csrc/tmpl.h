@@ -43,8 +43,10 @@ struct alignas(16) TNode {
 	u8 kind;	/* wildcard following the literal (TK_*) */
 	u8 cap;		/* 1 + plan slot receiving the wildcard, or 0 */
 	u8 poscap;	/* 1 + plan slot receiving the container that opens at
-			 * the literal's first byte, or 0 */
-	u8 pad[5];
+			 * byte `posoff` of the literal, or 0 */
+	u8 pad;
+	u16 posoff;
+	u16 pad2;
 };
 
 struct alignas(16) THdr {
