@@ -646,6 +646,12 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 				nw *= 2;
 			s->w_sslots = nw;
 		}
+		/* a fan-out plan runs a long stage list per record and tallies
+		 * many tuples: measured 1.2-2x faster on CTA tiles (whose
+		 * warps move through the stages together and whose tally cache
+		 * is larger) than on per-warp chunks */
+		if (plan->dev.nmetrics > 1)
+			s->kernel_pref = 1;
 		if (const char *ev = getenv("DNG_KERNEL")) {
 			/* tuning/testing: force one kernel geometry */
 			s->kernel_pref = !strcmp(ev, "tile") ? 1 :

@@ -450,6 +450,11 @@ struct TmplSmem {
 	{
 		return lds32(leaves + 4 * i);
 	}
+	__device__ __forceinline__ u32 pool32(u32 off) const
+	{
+		return lds32(pool + off);
+	}
+
 };
 
 /* one automaton step on a class code (see record.cuh fast_step) */

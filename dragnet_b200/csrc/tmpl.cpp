@@ -352,6 +352,50 @@ struct Trie {
 		return true;
 	}
 
+	/*
+	 * The byte offset at which a sibling group is dispatched: all literals
+	 * reach it and it tells the most siblings apart (-1: no dispatch).
+	 */
+	int disc_offset(const std::vector<int> &kids) const {
+		if (kids.size() < 2)
+			return -1;
+		size_t minl = (size_t)-1;
+		for (int k : kids)
+			minl = std::min(minl, nodes[k].lit.size());
+		int best = -1;
+		size_t bestn = 1;
+		for (size_t o = 0; o < minl && o < 0xffff; o++) {
+			bool seen[256] = { false };
+			size_t n = 0;
+			for (int k : kids) {
+				u8 b = (u8)nodes[k].lit[o];
+				if (!seen[b]) {
+					seen[b] = true;
+					n++;
+				}
+			}
+			if (n > bestn) {
+				bestn = n;
+				best = (int)o;
+			}
+		}
+		return best;
+	}
+
+	/* the siblings the matcher tries, in its order, for a record whose
+	 * literal at this place is `lit` */
+	std::vector<int> tried(const std::vector<int> &kids,
+	    const std::string &lit) const {
+		int o = disc_offset(kids);
+		if (o < 0)
+			return kids;
+		std::vector<int> out;
+		for (int k : kids)
+			if ((size_t)o < lit.size() && nodes[k].lit[o] == lit[o])
+				out.push_back(k);
+		return out;
+	}
+
 	/* does matching t's own shape leave every set slot filled from the
 	 * segment the parser took it from? */
 	bool verify(const PTmpl &t) const {
@@ -362,7 +406,7 @@ struct Trie {
 		for (size_t i = 0; i < t.segs.size(); i++) {
 			const PSeg &g = t.segs[i];
 			int hit = -1;
-			for (int k : nodes[cur].kids) {
+			for (int k : tried(nodes[cur].kids, g.lit)) {
 				if (nodes[k].lit == g.lit && nodes[k].kind == g.kind) {
 					hit = k;
 					break;
@@ -395,12 +439,21 @@ struct Trie {
 	}
 };
 
+size_t disp_bytes(const Trie &tr)
+{
+	size_t n = 0;
+	for (const BNode &b : tr.nodes)
+		if (tr.disc_offset(b.kids) >= 0)
+			n += (4 + 4 * b.kids.size() + 15) & ~(size_t)15;
+	return n;
+}
+
 size_t blob_bytes(const Trie &tr)
 {
-	size_t nn = tr.nodes.size() - 1;
+	size_t nn = tr.nodes.size() - 1 + (tr.nodes[0].kids.size() > 1 ? 1 : 0);
 	size_t n = sizeof (THdr) + nn * sizeof (TNode) + 4 * tr.leaf_mask.size();
 	n = (n + 15) & ~(size_t)15;
-	return ((n + tr.pool + 15) & ~(size_t)15);
+	return ((n + tr.pool + disp_bytes(tr) + 15) & ~(size_t)15);
 }
 
 bool build_trie(const std::vector<PTmpl> &ts, Trie &tr, size_t max_bytes)
@@ -412,7 +465,8 @@ bool build_trie(const std::vector<PTmpl> &ts, Trie &tr, size_t max_bytes)
 		if (!tr.verify(t))
 			return false;
 	return tr.nodes.size() - 1 <= TMPL_MAX_NODES &&
-	    tr.pool <= TMPL_MAX_POOL && tr.leaf_mask.size() <= TMPL_MAX_LEAVES &&
+	    tr.pool + disp_bytes(tr) <= TMPL_MAX_POOL &&
+	    tr.leaf_mask.size() <= TMPL_MAX_LEAVES &&
 	    blob_bytes(tr) <= max_bytes;
 }
 
@@ -445,10 +499,15 @@ void tmpl_build(const std::vector<TCandidate> &cands,
 
 	/* number the nodes: the children of one node are consecutive and
 	 * chained through `alt`; the root's first child is node 0 */
-	size_t nn = tr.nodes.size() - 1;
+	const bool synth_root = tr.nodes[0].kids.size() > 1;
+	size_t nn = tr.nodes.size() - 1 + (synth_root ? 1 : 0);
 	std::vector<int> index(tr.nodes.size(), -1);
 	std::vector<int> order;
 	std::vector<int> queue(1, 0);
+	if (synth_root) {
+		index[0] = 0;		/* the empty node the top-level shapes hang off */
+		order.push_back(0);
+	}
 	for (size_t q = 0; q < queue.size(); q++) {
 		for (int k : tr.nodes[queue[q]].kids) {
 			index[k] = (int)order.size();
@@ -457,20 +516,45 @@ void tmpl_build(const std::vector<TCandidate> &cands,
 		}
 	}
 	std::vector<TNode> out(nn);
+	if (synth_root) {
+		out[0].alt = (u16)TN_NOALT;
+		out[0].disp = TN_NODISP;
+		out[0].next = (u16)index[tr.nodes[0].kids[0]];
+	}
 	std::string pool;
 	for (size_t q = 0; q < queue.size(); q++) {
 		const std::vector<int> &kids = tr.nodes[queue[q]].kids;
+		/* dispatch table of this sibling group */
+		const int disc = tr.disc_offset(kids);
+		u16 disp = TN_NODISP;
+		if (disc >= 0) {
+			std::vector<u32> ents;
+			bool seen[256] = { false };
+			for (int k : kids) {
+				u8 b = (u8)tr.nodes[k].lit[disc];
+				if (!seen[b]) {
+					seen[b] = true;
+					ents.push_back((u32)b | ((u32)index[k] << 16));
+				}
+			}
+			disp = (u16)(pool.size() / 4);
+			u32 head = (u32)disc | ((u32)ents.size() << 16);
+			pool.append((const char *)&head, 4);
+			pool.append((const char *)ents.data(), 4 * ents.size());
+			pool.append((16 - pool.size() % 16) % 16, '\0');
+		}
+		if (index[queue[q]] >= 0)
+			out[index[queue[q]]].disp = disp;
 		for (size_t j = 0; j < kids.size(); j++) {
 			const BNode &b = tr.nodes[kids[j]];
 			TNode &o = out[index[kids[j]]];
-			memset(&o, 0, sizeof (o));
 			o.lit = (u16)pool.size();
 			o.len = (u16)b.lit.size();
 			for (size_t k = 0; k < b.lit.size(); k += 4) {
 				u32 v = 0, mk = 0;
-				for (size_t j = 0; j < 4 && k + j < b.lit.size(); j++) {
-					v |= (u32)(u8)b.lit[k + j] << (8 * j);
-					mk |= 0xffu << (8 * j);
+				for (size_t x = 0; x < 4 && k + x < b.lit.size(); x++) {
+					v |= (u32)(u8)b.lit[k + x] << (8 * x);
+					mk |= 0xffu << (8 * x);
 				}
 				pool.append((const char *)&v, 4);
 				pool.append((const char *)&mk, 4);
@@ -480,8 +564,17 @@ void tmpl_build(const std::vector<TCandidate> &cands,
 			o.cap = b.cap;
 			o.poscap = b.poscap;
 			o.posoff = b.posoff;
-			o.alt = j + 1 < kids.size() ? (u16)index[kids[j + 1]] :
-			    (u16)TN_NOALT;
+			o.disp = TN_NODISP;	/* filled in when its children are emitted */
+			/* next sibling the matcher may try after this one:
+			 * with a dispatch table, only one with the same byte */
+			o.alt = (u16)TN_NOALT;
+			for (size_t x = j + 1; x < kids.size(); x++) {
+				if (disc >= 0 && tr.nodes[kids[x]].lit[disc] !=
+				    b.lit[disc])
+					continue;
+				o.alt = (u16)index[kids[x]];
+				break;
+			}
 			o.next = b.leaf >= 0 ? (u16)(TN_LEAF | b.leaf) :
 			    (u16)index[b.kids[0]];
 		}
@@ -490,8 +583,8 @@ void tmpl_build(const std::vector<TCandidate> &cands,
 	memset(&h, 0, sizeof (h));
 	h.nnodes = (u16)nn;
 	h.nleaves = (u16)tr.leaf_mask.size();
-	h.leaf_off = (u32)(sizeof (THdr) + nn * sizeof (TNode));
-	h.pool_off = (h.leaf_off + 4 * h.nleaves + 15) & ~15u;
+	h.leaf_off = (u16)(sizeof (THdr) + nn * sizeof (TNode));
+	h.pool_off = (u16)((h.leaf_off + 4 * h.nleaves + 15) & ~15u);
 	h.bytes = (u32)((h.pool_off + pool.size() + 15) & ~(size_t)15);
 	blob.assign(h.bytes, 0);
 	memcpy(blob.data(), &h, sizeof (h));

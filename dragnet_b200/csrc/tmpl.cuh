@@ -68,6 +68,28 @@ DNG_HD u32 low_flag_byte(u32 m)
 }
 
 /*
+ * Which of a sibling group's nodes can match a record whose byte at the
+ * group's dispatch offset is what it is (tmpl.h THdr): the node, or TN_NOALT.
+ */
+template <class M>
+DNG_HD u32 tmpl_dispatch(M &m, u32 disp, u32 p, u32 len)
+{
+	const u32 head = m.pool32(4 * disp);
+	const u32 k = head & 0xffff, n = head >> 16;
+	if (p + k >= len)
+		return TN_NOALT;
+	const u32 b = m.byte(p + k);
+	u32 node = TN_NOALT;
+#pragma unroll 1
+	for (u32 i = 0; i < n; i++) {
+		const u32 e = m.pool32(4 * disp + 4 + 4 * i);
+		if ((e & 0xff) == b)
+			node = e >> 16;
+	}
+	return node;
+}
+
+/*
  * Every lane of the warp must call this (active = false for lanes without a
  * record): the node loop runs until no lane is active.
  */
@@ -217,6 +239,7 @@ DNG_HD bool tmpl_match(M &m, u32 len, RecState &R, bool active)
 			if (cap)
 				R.slots[cap - 1] = val;
 			p = q;
+			const u32 disp = nd.w >> 16;
 			if (succ & TN_LEAF) {
 				active = false;
 				if (p == len) {
@@ -226,6 +249,13 @@ DNG_HD bool tmpl_match(M &m, u32 len, RecState &R, bool active)
 				}
 			}
 			nd = nx;
+			if (disp != TN_NODISP) {
+				/* several children: straight to the one this
+				 * record's byte selects */
+				const u32 ch = tmpl_dispatch(m, disp, p, len);
+				active = ch != TN_NOALT;
+				nd = m.node(active ? ch : 0);
+			}
 		}
 		}
 	}
@@ -263,6 +293,11 @@ struct TmplHostMem {
 	u32 leaf(u32 i) const {
 		u32 v;
 		memcpy(&v, blob + ((const THdr *)blob)->leaf_off + 4 * i, 4);
+		return v;
+	}
+	u32 pool32(u32 off) const {
+		u32 v;
+		memcpy(&v, blob + ((const THdr *)blob)->pool_off + off, 4);
 		return v;
 	}
 };

@@ -31,7 +31,7 @@
 namespace dng {
 
 enum : u8 { TK_NONE = 0, TK_STR = 1, TK_BARE = 2 };
-enum : u16 { TN_LEAF = 0x8000, TN_NOALT = 0xffff };
+enum : u16 { TN_LEAF = 0x8000, TN_NOALT = 0xffff, TN_NODISP = 0xffff };
 
 struct alignas(16) TNode {
 	u16 lit;	/* literal: pool offset (16-byte aligned) of ceil(len/8)
@@ -46,14 +46,26 @@ struct alignas(16) TNode {
 			 * byte `posoff` of the literal, or 0 */
 	u8 pad;
 	u16 posoff;
-	u16 pad2;
+	u16 disp;	/* dispatch table of this node's children (pool offset
+			 * / 4), or TN_NODISP: see THdr */
 };
 
+/*
+ * Siblings (the children of one node, or the root's) are alternatives at the
+ * same place in the record.  Where their literals all reach some byte offset k
+ * and differ there, a dispatch table in the pool -- { k | n << 16 } then n
+ * entries { byte | node << 16 } -- sends a record straight to the first
+ * sibling that can match (its `alt` chain then holds only siblings with the
+ * same byte at k); a byte without an entry matches none.  Matching starts at
+ * node 0: the only top-level shape's first node, or, when there are several,
+ * an empty node whose children they are.
+ */
 struct alignas(16) THdr {
 	u32 bytes;	/* whole blob, multiple of 16 */
 	u16 nnodes, nleaves;
-	u32 leaf_off;	/* byte offset of the leaf table */
-	u32 pool_off;	/* byte offset of the literal pool */
+	u16 leaf_off;	/* byte offset of the leaf table */
+	u16 pool_off;	/* byte offset of the literal pool */
+	u16 pad[2];
 };
 
 enum : u32 {

@@ -72,7 +72,7 @@ int main(int argc, char **argv)
 			res[i].set_mask = TR.set_mask;
 			memcpy(res[i].slots, TR.slots, sizeof (TR.slots));
 		}
-		tmpl_build(cands, res, 1 << 20, blob, nullptr);
+		tmpl_build(cands, res, 60000, blob, nullptr);
 		if (getenv("DNG_HOSTCHECK_TMPL_DEBUG"))
 			fprintf(stderr, "tmpl: %zu candidates, blob %zu bytes, "
 			    "%u nodes, %u leaves\n", cands.size(), blob.size(),
