@@ -1,25 +1,34 @@
 /*
- * scan_kernel.cuh: the fused sm_100a scan kernel.
+ * scan_kernel.cuh: the fused sm_100a scan kernels.
  *
  * One launch = one pass of dragnet's raw-scan pipeline over a byte range that
  * is resident in HBM:
  *
- *   lstream line split      (lib/format-json.js:32-33)   newline index per tile
- *   JSON.parse + adapter    (lib/format-json.js:34-46)   parse_record()
- *   krill filters, dates,   (lib/stream-scan.js:56-86)   process_record()
- *   time bounds
- *   skinner aggregator      (lib/dragnet-impl.js:48-51)  shared-memory hash
- *                                                        table -> global table
+ *   lstream line split      (lib/format-json.js:32-33)   newline index
+ *   JSON.parse + adapter    (lib/format-json.js:34-46)   tmpl_match() ->
+ *                                                        fast_step() ->
+ *                                                        parse_record()
+ *   krill filters, dates,   (lib/stream-scan.js:56-86)   prepare_record(),
+ *   time bounds                                          process_metric()
+ *   skinner aggregator      (lib/dragnet-impl.js:48-51)  shared-memory tally
+ *                                                        cache -> global table
  *
- * Layout: persistent CTAs (2 per SM).  A CTA repeatedly takes a TILE of input,
- * stages [tile - PRELAP, tile + TILE) into shared memory with one TMA bulk
- * copy (cp.async.bulk + mbarrier), indexes the newlines in its tile (a tile
- * owns the records that END in it), then each thread parses whole records out
- * of shared memory.  Group keys are counted in a per-CTA shared-memory hash
- * table (exact: key bytes are compared, hashes only pick the slot) that is
- * flushed once per launch into the global table with 64-bit atomics.
- * Input is read from HBM exactly once (+PRELAP/TILE overlap); no intermediate
- * columns are written.
+ * Two geometries over the same per-record code (scan_record, scan_tail,
+ * scan_epilogue), one persistent 768-thread CTA per SM either way:
+ *
+ *   scan_kernel_w  every warp stages its own small chunk (TMA bulk copy into
+ *                  a private slice of shared memory, its own mbarrier), indexes
+ *                  it with shuffles and walks its records: no CTA barrier in
+ *                  the loop.  For input with short lines.
+ *   scan_kernel    the CTA stages a 156 KB tile, indexes it with a block scan
+ *                  and its threads take one record each.  Any line length.
+ *
+ * A tile / chunk owns the records that END in it and stages a pre-lap before
+ * itself for the record that straddles its start.  Group keys are counted in a
+ * per-CTA shared-memory tally cache (exact: key bytes are compared, hashes
+ * only pick the slot) that is flushed once per launch into the global table
+ * with 64-bit atomics.  Input is read from HBM once (+ the pre-laps); no
+ * intermediate columns are written.
  */
 #ifndef DNG_SCAN_KERNEL_CUH
 #define DNG_SCAN_KERNEL_CUH
@@ -1064,6 +1073,35 @@ scan_kernel(const ScanArgs a)
 	scan_epilogue(a, P, stab, C, s_mctr, nlong, ntmpl);
 }
 
+/*
+ * Newlines in a lane's slice [c0, c1) of the window at shared address sbase
+ * (bytes before `lower` do not count): their number, and << 16 the mask of the
+ * 16-byte words that hold one.  Out of line on purpose: inlined into the
+ * kernel, the loop's handful of live values were spilled to local memory and
+ * reloaded on every iteration.
+ */
+__device__ __noinline__ u32 slice_newlines(u32 sbase, u32 c0, u32 c1, u32 lower)
+{
+	u32 cnt = 0, hot = 0;
+	for (u32 p = c0; p < c1; p += 16) {
+		const uint4 v = lds128(sbase + p);
+		u32 m0 = nl_mask(v.x), m1 = nl_mask(v.y);
+		u32 m2 = nl_mask(v.z), m3 = nl_mask(v.w);
+		if (p + 16 > c1 || p < lower) {
+			/* partial word: keep only bytes in [lower, c1) */
+			m0 &= byte_range_mask(p, lower, c1);
+			m1 &= byte_range_mask(p + 4, lower, c1);
+			m2 &= byte_range_mask(p + 8, lower, c1);
+			m3 &= byte_range_mask(p + 12, lower, c1);
+		}
+		const u32 k = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+		cnt += k;
+		if (k)
+			hot |= 1u << ((p - c0) >> 4);
+	}
+	return cnt | (hot << 16);
+}
+
 /* ---- the per-warp kernel ---------------------------------------------------- */
 
 /*
@@ -1209,24 +1247,10 @@ scan_kernel_w(const ScanArgs a)
 		u32 c0 = off0 + lane * a.wslice, c1 = c0 + a.wslice;
 		if (c1 > wlen)
 			c1 = wlen;
-		u32 cnt = 0;
-		u32 hot = 0;		/* bit j: 16-byte word j holds a newline */
-		for (u32 p = c0; p < c1; p += 16) {
-			uint4 v = *(const uint4 *)(sdata + p);
-			u32 m0 = nl_mask(v.x), m1 = nl_mask(v.y);
-			u32 m2 = nl_mask(v.z), m3 = nl_mask(v.w);
-			if (p + 16 > c1 || p < lower) {
-				/* partial word: keep only bytes in [lower, c1) */
-				m0 &= byte_range_mask(p, lower, c1);
-				m1 &= byte_range_mask(p + 4, lower, c1);
-				m2 &= byte_range_mask(p + 8, lower, c1);
-				m3 &= byte_range_mask(p + 12, lower, c1);
-			}
-			u32 k = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-			cnt += k;
-			if (k)
-				hot |= 1u << ((p - c0) >> 4);
-		}
+		/* bit j of hot: 16-byte word j of the slice holds a newline */
+		const u32 sn = slice_newlines(smem_u32(sdata), c0, c1, lower);
+		u32 cnt = sn & 0xffff;
+		const u32 hot = sn >> 16;
 		/* an unterminated final line ends at a virtual newline */
 		const bool vnl = a.final && we == a.nbytes && lane == 31 &&
 		    a.nbytes > a.start && wlen > 0 && wlen > lower &&
