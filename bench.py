@@ -294,8 +294,10 @@ def gpu_arm(args, rank, local_rank, world):
         s.set_stream(stream)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
+        em = torch.cuda.Event(enable_timing=True)
         e0.record()
         feed(s)
+        em.record()
         if comm is not None and merge:
             out = ctypes.c_void_p()
             ctr = native.DngCounters()
@@ -315,6 +317,7 @@ def gpu_arm(args, rank, local_rank, world):
         st = s.kernel_stats()
         st.update(s.template_stats())
         ms = e0.elapsed_time(e1)
+        st['after_feed_ms'] = em.elapsed_time(e1)   # finish / cross-GPU merge
         s.close()
         return pts, counters, st, ms
 
@@ -355,20 +358,23 @@ def gpu_arm(args, rank, local_rank, world):
         sampler.start()
         t0 = time.perf_counter()
         dev_ms, kern_ms, kern_bytes, launches = 0.0, 0.0, 0, 0
+        tail_ms = 0.0
         for _ in range(steps):
             res = one_scan(feed)
             dev_ms += res[3]
+            tail_ms += res[2]['after_feed_ms']
             kern_ms += res[2]['kernel_ms']
             kern_bytes += res[2]['kernel_bytes']
             launches += res[2]['launches']
         barrier()
         wall = time.perf_counter() - t0
         clocks = sampler.stop()
-        t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64,
+        t = torch.tensor([dev_ms, wall * 1e3, tail_ms], dtype=torch.float64,
                          device='cuda:%d' % dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return {'dev_ms': float(t[0]), 'wall_ms': float(t[1]),
+                'tail_ms': float(t[2]),
                 'kernel_ms': kern_ms, 'kernel_bytes': kern_bytes,
                 'launches': launches, 'clocks': clocks, 'last': res}
 
@@ -477,6 +483,8 @@ def gpu_arm(args, rank, local_rank, world):
         'unit': 'records/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_per_step,
         'wall_ms_per_step': R['wall_ms'] / args.steps,
+        # finish + (N>1) the NCCL merge of the tallies, inside ms_per_step
+        'finish_merge_ms_per_step': R['tail_ms'] / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'u8', 'data': 'synthetic',
         'config': {

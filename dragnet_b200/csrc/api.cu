@@ -128,6 +128,18 @@ void set_err(char *err, size_t errlen, const char *fmt, const char *a = "")
 
 } /* namespace */
 
+/* the same buffer cache for the library's other translation units (merge.cu) */
+cudaError_t dng_cached_alloc(int device, void **p, size_t n)
+{
+	return cached_alloc(device, p, n);
+}
+
+void dng_cached_free(void *p)
+{
+	cached_free(p);
+}
+
+
 struct dng_scan {
 	dng_plan plan;
 	int device = 0;

@@ -30,6 +30,20 @@
 #include "result.h"
 #include "plan.h"
 
+/* api.cu: scratch buffers come from (and go back to) the per-process cache;
+ * cudaMalloc/cudaFree per merge cost milliseconds and serialise across the
+ * processes of a multi-GPU job */
+cudaError_t dng_cached_alloc(int device, void **p, size_t n);
+void dng_cached_free(void *p);
+
+static size_t pow2_at_least(size_t n)
+{
+	size_t c = 4096;
+	while (c < n)
+		c <<= 1;
+	return c;
+}
+
 namespace {
 
 bool dict_parse(const void *buf, size_t len, std::vector<std::string> &keys)
@@ -362,7 +376,7 @@ int dng_merge_nccl(dng_scan *scan, dng_comm *c, int root, dng_result **out,
 
 	/* (a) all-gather dictionary sizes, then the padded dictionaries */
 	unsigned long long *d_sz = nullptr;
-	cudaMalloc(&d_sz, sizeof (unsigned long long) * (c->nranks + 1));
+	dng_cached_alloc(c->device, (void **)&d_sz, 4096);
 	unsigned long long mysz = dlen;
 	cudaMemcpyAsync(d_sz + c->nranks, &mysz, 8, cudaMemcpyHostToDevice,
 	    c->stream);
@@ -377,8 +391,9 @@ int dng_merge_nccl(dng_scan *scan, dng_comm *c, int root, dng_result **out,
 		maxsz = std::max(maxsz, (size_t)v);
 	maxsz = (maxsz + 15) & ~(size_t)15;
 	unsigned char *d_all = nullptr, *d_mine = nullptr;
-	cudaMalloc(&d_all, maxsz * c->nranks);
-	cudaMalloc(&d_mine, maxsz);
+	dng_cached_alloc(c->device, (void **)&d_all,
+	    pow2_at_least(maxsz * c->nranks));
+	dng_cached_alloc(c->device, (void **)&d_mine, pow2_at_least(maxsz));
 	cudaMemsetAsync(d_mine, 0, maxsz, c->stream);
 	cudaMemcpyAsync(d_mine, dict, dlen, cudaMemcpyHostToDevice, c->stream);
 	if (!nrc)
@@ -408,8 +423,8 @@ int dng_merge_nccl(dng_scan *scan, dng_comm *c, int root, dng_result **out,
 		rc = dng_result_dense(local, gdict, glen, vec.data(), G);
 	memcpy(vec.data() + G, &lc, sizeof (lc));
 	uint64_t *d_vec = nullptr, *d_red = nullptr;
-	cudaMalloc(&d_vec, vec.size() * 8);
-	cudaMalloc(&d_red, vec.size() * 8);
+	dng_cached_alloc(c->device, (void **)&d_vec, pow2_at_least(vec.size() * 8));
+	dng_cached_alloc(c->device, (void **)&d_red, pow2_at_least(vec.size() * 8));
 	cudaMemcpyAsync(d_vec, vec.data(), vec.size() * 8,
 	    cudaMemcpyHostToDevice, c->stream);
 	if (!rc && !nrc)
@@ -426,11 +441,11 @@ int dng_merge_nccl(dng_scan *scan, dng_comm *c, int root, dng_result **out,
 	} else {
 		cudaStreamSynchronize(c->stream);
 	}
-	cudaFree(d_sz);
-	cudaFree(d_all);
-	cudaFree(d_mine);
-	cudaFree(d_vec);
-	cudaFree(d_red);
+	dng_cached_free(d_sz);
+	dng_cached_free(d_all);
+	dng_cached_free(d_mine);
+	dng_cached_free(d_vec);
+	dng_cached_free(d_red);
 	dng_buf_free(gdict);
 	dng_result_destroy(local);
 	if (nrc)
