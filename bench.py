@@ -65,7 +65,13 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks/throttle reasons during the timed region."""
+    """nvidia-smi clocks/throttle reasons during the timed regions.
+
+    ONE nvidia-smi process for the whole run, started before any warm-up (its
+    start-up attaches to every GPU of the box and stalls CUDA calls for a
+    while: eight of them starting inside an 8-rank timed region cost 150 ms
+    per step), sampling all the GPUs of the job every 100 ms; a timed region
+    is marked and what was sampled since the mark is summarised."""
 
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,'
          'clocks_event_reasons.hw_slowdown,'
@@ -73,16 +79,18 @@ class ClockSampler(object):
          'clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index):
-        self.index = index
+    def __init__(self, indexes):
+        self.indexes = list(indexes)
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, text)
+        self.t0 = 0.0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '200'],
+                ['nvidia-smi', '-i', ','.join(str(i) for i in self.indexes),
+                 '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                 '-lms', '100'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -91,21 +99,22 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        self.t0 = time.time()
+
+    def since_mark(self):
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [],
                     'samples': 0}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        lines = [l for t, l in self.lines if t >= self.t0]
+        if not lines:            # region shorter than the sampling interval
+            lines = [l for _, l in self.lines[-len(self.indexes):]]
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
                  'sw_power_cap']
-        for l in self.lines:
+        for l in lines:
             f = [x.strip() for x in l.split(',')]
             if len(f) < 8:
                 continue
@@ -121,6 +130,15 @@ class ClockSampler(object):
         return {'sm_mhz': sm[len(sm) // 2] if sm else None,
                 'sm_max_mhz': max(mx) if mx else None,
                 'reasons': sorted(reasons), 'samples': len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.proc = None
 
 
 def canon(points):
@@ -247,6 +265,12 @@ def gpu_arm(args, rank, local_rank, world):
     plan_json = json.dumps(plan, separators=(',', ':'))
     rows = args.rows
     seed = 0xD5A60000 + rank
+    # clocks / throttle reasons of every GPU of the job, sampled by rank 0 from
+    # before the warm-up on (see ClockSampler)
+    sampler = None
+    if rank == 0:
+        sampler = ClockSampler(range(world))
+        sampler.start()
 
     # ---- the shard, generated in HBM --------------------------------------
     params = native.gen_params(seed=seed, total_records=rows)
@@ -354,8 +378,8 @@ def gpu_arm(args, rank, local_rank, world):
         for _ in range(warmup):
             res = one_scan(feed)
         barrier()
-        sampler = ClockSampler(dev)
-        sampler.start()
+        if sampler is not None:
+            sampler.mark()
         t0 = time.perf_counter()
         dev_ms, kern_ms, kern_bytes, launches = 0.0, 0.0, 0, 0
         tail_ms = 0.0
@@ -368,7 +392,7 @@ def gpu_arm(args, rank, local_rank, world):
             launches += res[2]['launches']
         barrier()
         wall = time.perf_counter() - t0
-        clocks = sampler.stop()
+        clocks = sampler.since_mark() if sampler is not None else None
         t = torch.tensor([dev_ms, wall * 1e3, tail_ms], dtype=torch.float64,
                          device='cuda:%d' % dev)
         if world > 1:
@@ -520,13 +544,15 @@ def gpu_arm(args, rank, local_rank, world):
                         'dng_scan_feed_pinned (H2D ring overlapped with the '
                         'scan kernel)' % (pool_rows, cycles)},
         'gpu_launches': R['launches'],
-        'clocks': R['clocks'],
+        'clocks': R['clocks'] if rank == 0 else None,
         'parity': parity,
         'merge_parity': merge_parity,
         'e2e_file': file_leg,
     }
     if cpu:
         line['cpu_baseline'] = cpu
+    if sampler is not None:
+        sampler.stop()
     print(json.dumps(line), flush=True)
     if comm is not None:
         L.dng_comm_destroy(comm)
