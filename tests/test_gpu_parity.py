@@ -351,3 +351,33 @@ def test_stream_that_turns_to_long_lines_switches_kernel(tmp_path):
     assert r.counters == exp_c
     if 'DNG_KERNEL' not in os.environ:
         assert r.stats['kernel'] == 'CTA tiles', r.stats
+
+
+def test_optional_fields_make_a_branching_trie(tmp_path):
+    """Four optional fields -> sixteen record shapes sharing prefixes (sibling
+    dispatch + alt chains in the template trie): all templated, answers equal
+    the oracle's."""
+    import random
+    from dragnet_b200 import datasource_gpu
+    rng = random.Random(11)
+    lines = []
+    for i in range(40000):
+        parts = [b'"id":%d' % i]
+        if rng.random() < 0.5:
+            parts.append(b'"a":"x%d"' % (i % 3))
+        if rng.random() < 0.5:
+            parts.append(b'"b":{"c":%d}' % (i % 4))
+        if rng.random() < 0.5:
+            parts.append(b'"d":null')
+        if rng.random() < 0.5:
+            parts.append(b'"e":[%d,"s"]' % (i % 2))
+        parts.append(b'"z":"end"')
+        lines.append(b'{' + b','.join(parts) + b'}')
+    path = _write(tmp_path, 'opt.log', lines)
+    plan = corpus.make_plan(['-b', 'a,b.c,d'])
+    exp_p, exp_c = cpp_engine(plan, [path], threads=4)
+    r = datasource_gpu.run_plan(plan, files=[path])
+    assert canon_points(r.points) == canon_points(exp_p)
+    assert r.counters == exp_c
+    assert r.stats['templates'] == 16, r.stats
+    assert r.stats['templated_records'] == len(lines), r.stats

@@ -59,3 +59,39 @@ def test_shapes_that_cannot_be_templates_fall_through(tmp_path):
     assert doc['counters']['invalid_json'] == 5
     doc, dbg = run_tmpl(corpus.make_plan(['-b', 'a,n']), str(p), tmp_path)
     assert doc['ntmpl'] == 80, (doc['ntmpl'], dbg)
+
+
+def test_optional_fields_make_a_branching_trie(tmp_path):
+    """Four optional fields -> sixteen shapes sharing prefixes: all of them are
+    templated (sibling dispatch + alt chains), and the answers are the
+    oracle's."""
+    import random
+    from engines import canon_points, hostcheck_engine, py_engine
+    rng = random.Random(11)
+    lines = []
+    for i in range(4000):
+        parts = [b'"id":%d' % i]
+        if rng.random() < 0.5:
+            parts.append(b'"a":"x%d"' % (i % 3))
+        if rng.random() < 0.5:
+            parts.append(b'"b":{"c":%d}' % (i % 4))
+        if rng.random() < 0.5:
+            parts.append(b'"d":null')
+        if rng.random() < 0.5:
+            parts.append(b'"e":[%d,"s"]' % (i % 2))
+        parts.append(b'"z":"end"')
+        lines.append(b'{' + b','.join(parts) + b'}')
+    p = tmp_path / 'opt.log'
+    p.write_bytes(b'\n'.join(lines) + b'\n')
+    plan = corpus.make_plan(['-b', 'a,b.c,d'])
+    doc, dbg = run_tmpl(plan, str(p), tmp_path)
+    assert doc['ntmpl'] == len(lines), (doc['ntmpl'], dbg)
+    assert '16 leaves' in dbg, dbg
+    os.environ['DNG_HOSTCHECK_TMPL'] = '1'
+    try:
+        act_p, act_c = hostcheck_engine(plan, [str(p)])
+    finally:
+        del os.environ['DNG_HOSTCHECK_TMPL']
+    exp_p, exp_c = py_engine(plan, [str(p)])
+    assert canon_points(act_p) == canon_points(exp_p)
+    assert act_c == exp_c
