@@ -171,6 +171,7 @@ struct dng_scan {
 	std::vector<cudaEvent_t> ev_pool;
 	double kernel_ms = 0;
 	uint64_t launches = 0, kernel_bytes = 0, bytes_fed = 0;
+	uint64_t aux_launches = 0;	/* resolve / find_nl / compact kernels */
 	cudaEvent_t ev_init = nullptr;	/* setup enqueued by dng_scan_open */
 	bool finished = false;
 	/* record templates (tmpl.h), learned from the head of the input */
@@ -336,6 +337,7 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 		e = cudaMemcpyAsync(d_offs, se.data(), se.size() * sizeof (u32),
 		    cudaMemcpyHostToDevice, s->stream);
 	if (e == cudaSuccess) {
+		s->aux_launches++;
 		resolve_pairs_kernel<<<1, 32, 0, s->stream>>>(s->d_plan, d_lines,
 		    d_offs, (u32)cands.size(), d_res);
 		e = cudaGetLastError();
@@ -1035,13 +1037,17 @@ int dng_scan_feed_device(dng_scan *s, const void *devbuf, size_t len)
 		CK(s, cudaMemcpyAsync(s->d_nl, init, sizeof (init),
 		    cudaMemcpyHostToDevice, s->stream));
 		if (attempt == 0) {
+			s->aux_launches++;
 			find_nl_kernel<<<64, 256, 0, s->stream>>>(d, 0,
 			    std::min<unsigned long long>(len, W), s->d_nl,
 			    s->d_nl + 1);
-			if (len > W)
+			if (len > W) {
+				s->aux_launches++;
 				find_nl_kernel<<<64, 256, 0, s->stream>>>(d,
 				    len - W, len, s->d_nl, s->d_nl + 1);
+			}
 		} else {
+			s->aux_launches++;
 			find_nl_kernel<<<1024, 256, 0, s->stream>>>(d, 0, len,
 			    s->d_nl, s->d_nl + 1);
 		}
@@ -1252,6 +1258,7 @@ int dng_scan_finish(dng_scan *s, dng_result **out)
 		CK(s, DEV_ALLOC(s, &d_out, cap_out * sizeof (OutEntry)));
 		CK(s, DEV_ALLOC(s, &d_n, 16));
 		CK(s, cudaMemsetAsync(d_n, 0, sizeof (u32), s->stream));
+		s->aux_launches++;
 		compact_kernel<<<256, 256, 0, s->stream>>>(s->tab.entries,
 		    s->tab.mask + 1, d_out, d_n);
 		std::vector<OutEntry> ents(n);
@@ -1310,6 +1317,11 @@ int dng_scan_template_stats(dng_scan *s, uint64_t *templates,
 	if (templated_records)
 		*templated_records = c;
 	return DNG_OK;
+}
+
+uint64_t dng_scan_launch_count(const dng_scan *s)
+{
+	return s ? s->launches + s->aux_launches : 0;
 }
 
 int dng_scan_kernel_kind(const dng_scan *s)

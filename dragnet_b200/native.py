@@ -77,6 +77,7 @@ _SIGS = [
     ('dng_scan_template_stats', ctypes.c_int,
      [_P, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     ('dng_scan_kernel_kind', ctypes.c_int, [_P]),
+    ('dng_scan_launch_count', ctypes.c_uint64, [_P]),
     ('dng_pinned_alloc', _P, [ctypes.c_size_t]),
     ('dng_pinned_free', None, [_P]),
     ('dng_result_count', ctypes.c_size_t, [_P]),
@@ -335,7 +336,8 @@ class Scan(object):
                                            ctypes.byref(n), ctypes.byref(b)),
                self.handle)
         return {'kernel_ms': ms.value, 'launches': int(n.value),
-                'kernel_bytes': int(b.value)}
+                'kernel_bytes': int(b.value),
+                'all_launches': int(lib().dng_scan_launch_count(self.handle))}
 
     def set_templates(self, enable):
         """Record templates on/off (default on); before the first feed."""

@@ -164,6 +164,10 @@ int dng_scan_template_stats(dng_scan *scan, uint64_t *templates,
  * tiles (any line length), 1 = per-warp chunks (short lines).
  */
 int dng_scan_kernel_kind(const dng_scan *scan);
+/* Every kernel this scan has launched so far: scan kernels plus the small
+ * ones around them (template resolution, newline search of device feeds,
+ * result compaction). */
+uint64_t dng_scan_launch_count(const dng_scan *scan);
 
 void *dng_pinned_alloc(size_t len);
 void dng_pinned_free(void *p);
