@@ -246,3 +246,59 @@ def scalar_lines():
     for i, f in enumerate(STR_FORMS):
         out.append(b'{"a":%d,"s":"' % (i % 7) + f + b'"}')
     return out
+
+
+# ---------------------------------------------------------------------------
+# template fuzz: a few record shapes, every line one of them with re-rolled
+# scalar values (nasty strings, every number form, bare-scalar type flips) and
+# a sprinkle of damage -- what the template matcher sees in the field
+# ---------------------------------------------------------------------------
+
+def _reroll(rng, v):
+    if isinstance(v, dict):
+        return {k: _reroll(rng, x) for k, x in v.items()}
+    if isinstance(v, list):
+        return [_reroll(rng, x) for x in v]
+    if isinstance(v, str):
+        return rng.choice(['GET', 'PUT', 'x', '', 'a b', '\u00e9', 'x"y', 'tab\t',
+                           '\U0001F600', '2014-05-01T00:00:00Z', '200', ' 12 ',
+                           '\\', '/', '\u20acuro' * 3, 'long' * 9])
+    return rng.choice([None, True, False, 0, -0.0, 7, -12, 123456789012345,
+                       1234567890123456, 0.5, 1e21, 1e-7, 1.5e300, 2e2, 4.35,
+                       100])
+
+
+def _dumps_shape(v, fmt, rng):
+    """Formatting (separators) is a property of the shape, not of the line."""
+    if isinstance(v, dict):
+        sep, col = fmt.choice([',', ', ']), fmt.choice([':', ': '])
+        return '{' + sep.join(json.dumps(k) + col + _dumps_shape(x, fmt, rng)
+                              for k, x in v.items()) + '}'
+    if isinstance(v, list):
+        return '[' + ','.join(_dumps_shape(x, fmt, rng) for x in v) + ']'
+    if isinstance(v, float) and rng.random() < 0.3 and v == int(v) and \
+            abs(v) < 1e15:
+        return rng.choice(['%d.0', '%de0', '%d.00E+0']) % int(v)
+    return json.dumps(v, ensure_ascii=rng.random() < 0.5)
+
+
+def template_fuzz_lines(seed, n, nshapes=6):
+    rng = random.Random(seed)
+    shapes = []
+    while len(shapes) < nshapes:
+        v = rand_json(rng)
+        if isinstance(v, dict) and len(v) >= 1:
+            shapes.append((v, rng.randrange(1 << 30)))
+    out = []
+    for _ in range(n):
+        v, fmt = rng.choice(shapes)
+        text = _dumps_shape(_reroll(rng, v), random.Random(fmt), rng)
+        r = rng.random()
+        if r < 0.03:
+            text = text[:rng.randrange(0, max(1, len(text)))]
+        elif r < 0.05:
+            text += rng.choice(['x', ',', '}', ' 1', ' '])
+        elif r < 0.07:
+            text = text.replace(':', ' :', 1)
+        out.append(text.encode('utf-8'))
+    return out

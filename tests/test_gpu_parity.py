@@ -381,3 +381,16 @@ def test_optional_fields_make_a_branching_trie(tmp_path):
     assert r.counters == exp_c
     assert r.stats['templates'] == 16, r.stats
     assert r.stats['templated_records'] == len(lines), r.stats
+
+
+@pytest.mark.parametrize('seed', range(3))
+def test_template_fuzz(seed, tmp_path):
+    """corpus.template_fuzz_lines through the GPU: shapes with re-rolled scalar
+    values and a little damage."""
+    path = _write(tmp_path, 'fz.log', corpus.template_fuzz_lines(100 + seed, 3000))
+    for argv, ds in corpus.EDGE_QUERIES[:30:5]:
+        plan = corpus.make_plan(argv, ds)
+        exp_p, exp_c = py_engine(plan, [path])
+        act_p, act_c = gpu_engine(plan, [path])
+        assert canon_points(act_p) == canon_points(exp_p), (seed, argv)
+        assert act_c == exp_c, (seed, argv)

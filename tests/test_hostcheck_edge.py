@@ -78,3 +78,12 @@ def test_scalar_forms_behind_one_template(tmp_path):
     for argv in (['-b', 'a'], ['-b', 's'], ['-b', 'a[aggr=quantize]'],
                  ['-b', 'a,s', '-f', '{"ge":["a",1]}']):
         _compare(corpus.make_plan(argv), path)
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_template_fuzz(seed, tmp_path):
+    """A few shapes, re-rolled scalars, some damage (corpus.template_fuzz_lines):
+    in template mode most lines meet a learned template."""
+    path = _write(tmp_path, 'fz.log', corpus.template_fuzz_lines(seed, 800))
+    for argv, ds in corpus.EDGE_QUERIES[:30:4]:
+        _compare(corpus.make_plan(argv, ds), path)
