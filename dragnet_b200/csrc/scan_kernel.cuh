@@ -824,7 +824,6 @@ scan_kernel(const ScanArgs a)
 	}
 	__syncthreads();
 	const DevPlan &P = *sp;		/* the plan, in shared memory */
-	const HotPlan &H = P.hot;	/* the lock-step loop's tables */
 
 	/* record templates, if the host learned any for this input */
 	const bool use_tmpl = a.tmpl_bytes != 0;
@@ -1275,7 +1274,6 @@ scan_kernel_w(const ScanArgs a)
 		 * pre-lap [lower, start0), which the lanes search together (32
 		 * bytes each, nearest the chunk first).
 		 */
-		const u32 start0 = off0 < lower ? lower : off0;
 		u32 beg0 = lower;
 		bool islong0 = false;
 		{

@@ -24,7 +24,26 @@
 #include "tmpl.h"
 #include "record.cuh"
 
+/* unroll factors of the matcher's two inner loops (measured: see DESIGN.md) */
+#ifndef DNG_LIT_UNROLL
+#define DNG_LIT_UNROLL 1
+#endif
+#ifndef DNG_STR_UNROLL
+#define DNG_STR_UNROLL 2
+#endif
+
+/* unroll factors of the matcher's two inner loops (measured: see DESIGN.md) */
+#ifndef DNG_LIT_UNROLL
+#define DNG_LIT_UNROLL 1
+#endif
+#ifndef DNG_STR_UNROLL
+#define DNG_STR_UNROLL 2
+#endif
+
 namespace dng {
+
+static constexpr int TM_LIT_UNROLL = DNG_LIT_UNROLL;
+static constexpr int TM_STR_UNROLL = DNG_STR_UNROLL;
 
 struct TQuad { u32 x, y, z, w; };	/* one TNode as four words */
 
@@ -111,7 +130,7 @@ DNG_HD bool tmpl_match(M &m, u32 len, RecState &R, bool active)
 			 * the literal's padding is masked out, so no tail case */
 			typename M::Cur c = m.cursor(p);
 			u32 diff = 0;
-#pragma unroll 1
+#pragma unroll TM_LIT_UNROLL
 			for (u32 k = 0; k < L; k += 8) {
 				const TQuad lq = m.lit2(lit + 2 * k);
 				const u32 d0 = c.next(), d1 = c.next();
@@ -129,7 +148,7 @@ DNG_HD bool tmpl_match(M &m, u32 len, RecState &R, bool active)
 			for (;;) {
 				typename M::Cur c = m.cursor(e);
 				u32 hit, w;
-#pragma unroll 2
+#pragma unroll TM_STR_UNROLL
 				for (;;) {
 					w = c.next();
 					hit = tz_low(w ^ 0x22222222u) |
