@@ -776,6 +776,35 @@ __device__ __forceinline__ void scan_epilogue(const ScanArgs &a,
 	}
 }
 
+/*
+ * Newlines in a lane's slice [c0, c1) of the window at shared address sbase
+ * (bytes before `lower` do not count): their number, and << 16 the mask of the
+ * 16-byte words that hold one.  Out of line on purpose: inlined into the
+ * kernel, the loop's handful of live values were spilled to local memory and
+ * reloaded on every iteration.
+ */
+__device__ __noinline__ u32 slice_newlines(u32 sbase, u32 c0, u32 c1, u32 lower)
+{
+	u32 cnt = 0, hot = 0;
+	for (u32 p = c0; p < c1; p += 16) {
+		const uint4 v = lds128(sbase + p);
+		u32 m0 = nl_mask(v.x), m1 = nl_mask(v.y);
+		u32 m2 = nl_mask(v.z), m3 = nl_mask(v.w);
+		if (p + 16 > c1 || p < lower) {
+			/* partial word: keep only bytes in [lower, c1) */
+			m0 &= byte_range_mask(p, lower, c1);
+			m1 &= byte_range_mask(p + 4, lower, c1);
+			m2 &= byte_range_mask(p + 8, lower, c1);
+			m3 &= byte_range_mask(p + 12, lower, c1);
+		}
+		const u32 k = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+		cnt += k;
+		if (k)
+			hot |= 1u << ((p - c0) >> 4);
+	}
+	return cnt | (hot << 16);
+}
+
 /* ---- the kernel ------------------------------------------------------------ */
 
 __global__ void __launch_bounds__(DNG_NT, DNG_CTAS_PER_SM)
@@ -904,24 +933,10 @@ scan_kernel(const ScanArgs a)
 		u32 c0 = off0 + tid * CH, c1 = c0 + CH;
 		if (c1 > wlen)
 			c1 = wlen;
-		u32 cnt = 0;
-		u32 hot = 0;		/* bit j: 16-byte word j holds a newline */
-		for (u32 p = c0; p < c1; p += 16) {
-			uint4 v = *(const uint4 *)(sdata + p);
-			u32 m0 = nl_mask(v.x), m1 = nl_mask(v.y);
-			u32 m2 = nl_mask(v.z), m3 = nl_mask(v.w);
-			if (p + 16 > c1 || p < lower) {
-				/* partial word: keep only bytes in [lower, c1) */
-				m0 &= byte_range_mask(p, lower, c1);
-				m1 &= byte_range_mask(p + 4, lower, c1);
-				m2 &= byte_range_mask(p + 8, lower, c1);
-				m3 &= byte_range_mask(p + 12, lower, c1);
-			}
-			u32 k = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-			cnt += k;
-			if (k)
-				hot |= 1u << ((p - c0) >> 4);
-		}
+		/* bit j of hot: 16-byte word j of the slice holds a newline */
+		const u32 sn = slice_newlines(smem_u32(sdata), c0, c1, lower);
+		u32 cnt = sn & 0xffff;
+		const u32 hot = sn >> 16;
 		/* an unterminated final line ends at a virtual newline */
 		const bool vnl = a.final && we == a.nbytes && tid == DNG_NT - 1 &&
 		    a.nbytes > a.start && wlen > 0 && wlen > lower &&
@@ -1070,35 +1085,6 @@ scan_kernel(const ScanArgs a)
 #endif
 
 	scan_epilogue(a, P, stab, C, s_mctr, nlong, ntmpl);
-}
-
-/*
- * Newlines in a lane's slice [c0, c1) of the window at shared address sbase
- * (bytes before `lower` do not count): their number, and << 16 the mask of the
- * 16-byte words that hold one.  Out of line on purpose: inlined into the
- * kernel, the loop's handful of live values were spilled to local memory and
- * reloaded on every iteration.
- */
-__device__ __noinline__ u32 slice_newlines(u32 sbase, u32 c0, u32 c1, u32 lower)
-{
-	u32 cnt = 0, hot = 0;
-	for (u32 p = c0; p < c1; p += 16) {
-		const uint4 v = lds128(sbase + p);
-		u32 m0 = nl_mask(v.x), m1 = nl_mask(v.y);
-		u32 m2 = nl_mask(v.z), m3 = nl_mask(v.w);
-		if (p + 16 > c1 || p < lower) {
-			/* partial word: keep only bytes in [lower, c1) */
-			m0 &= byte_range_mask(p, lower, c1);
-			m1 &= byte_range_mask(p + 4, lower, c1);
-			m2 &= byte_range_mask(p + 8, lower, c1);
-			m3 &= byte_range_mask(p + 12, lower, c1);
-		}
-		const u32 k = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-		cnt += k;
-		if (k)
-			hot |= 1u << ((p - c0) >> 4);
-	}
-	return cnt | (hot << 16);
 }
 
 /* ---- the per-warp kernel ---------------------------------------------------- */
