@@ -30,6 +30,7 @@
 #include "plan.h"
 #include "result.h"
 #include "scan_kernel.cuh"
+#include "fast_kernel.cuh"
 #include "gen.cuh"
 
 using namespace dng;
@@ -179,7 +180,7 @@ struct dng_scan {
 	/* kernel geometry: per-warp chunks for short lines, CTA tiles otherwise */
 	bool warp_kernel = false;
 	u32 wslice = DNG_W_SLICE_MAX;	/* bytes per lane of a warp's chunk */
-	int kernel_pref = 0;		/* DNG_KERNEL: 0 auto, 1 tile, 2 warp */
+	int kernel_pref = 0;		/* DNG_KERNEL: 0 auto, 1 tile, 2 warp, 3 fast */
 	u32 w_sslots = 0, w_s1slots = 0;
 	/* counters of finished launches, copied to pinned memory after every
 	 * launch: lets the host notice that the input changed character */
@@ -189,6 +190,18 @@ struct dng_scan {
 	int relearns = 0;
 	u8 *d_tmpl = nullptr;
 	u32 tmpl_bytes = 0, ntemplates = 0;
+	/* the F path (fast.h): its plan, its templates, its miss list */
+	FPlan fplan;
+	FPlan *d_fplan = nullptr;
+	u8 *d_ftmpl = nullptr;
+	u32 ftmpl_bytes = 0, nftemplates = 0, ftmpl_leaf_off = 0, ftmpl_pool_off = 0;
+	bool f_kernel = false;
+	u32 f_nsl = 13;			/* 16-byte units per lane slice */
+	u32 f_smem_max = 0;		/* dynamic shared memory a CTA may ask for */
+	MissEnt *d_miss = nullptr;
+	u32 *d_miss_n = nullptr;
+	u32 miss_cap = 0;
+	unsigned long long seen_tmpl = 0;
 	std::string err;
 	int err_code = 0;
 
@@ -239,6 +252,49 @@ __global__ void resolve_pairs_kernel(const DevPlan *plan, const u8 *lines,
 	out[i].set_mask = R.set_mask;
 	for (int k = 0; k < MAX_SLOTS; k++)
 		out[i].slots[k] = ((R.set_mask >> k) & 1) ? R.slots[k] : 0;
+}
+
+/*
+ * The F path's templates (fast.h): the same candidates, their captures indexed
+ * by path, compact literals.  The F kernel is chosen when they cover the
+ * sample (results never depend on that choice, only the speed does).
+ */
+int learn_ftemplates(dng_scan *s, const std::vector<TCandidate> &cands,
+    const std::vector<TResolved> &res, size_t sampled_lines)
+{
+	std::vector<TResolved> fres(res.size());
+	for (size_t i = 0; i < res.size(); i++)
+		fplan_resolve(s->plan.dev, res[i], fres[i]);
+	std::vector<u8> blob, accepted;
+	u32 nt = 0;
+	tmpl_build(cands, fres, TMPL_RESERVE, blob, &nt, true, &accepted);
+	cached_free(s->d_ftmpl);
+	s->d_ftmpl = nullptr;
+	s->ftmpl_bytes = 0;
+	s->nftemplates = 0;
+	if (!blob.empty()) {
+		const THdr *th = (const THdr *)blob.data();
+		s->ftmpl_leaf_off = th->leaf_off;
+		s->ftmpl_pool_off = th->pool_off;
+	}
+	size_t covered = 0;
+	for (size_t i = 0; i < cands.size(); i++)
+		if (accepted[i])
+			covered += cands[i].count;
+	if (!blob.empty()) {
+		size_t padded = (blob.size() + 127) & ~(size_t)127;
+		blob.resize(padded, 0);
+		CK(s, DEV_ALLOC(s, &s->d_ftmpl, padded));
+		CK(s, cudaMemcpyAsync(s->d_ftmpl, blob.data(), padded,
+		    cudaMemcpyHostToDevice, s->stream));
+		CK(s, cudaStreamSynchronize(s->stream));
+		s->ftmpl_bytes = (u32)padded;
+		s->nftemplates = nt;
+	}
+	if (s->kernel_pref == 0)
+		s->f_kernel = s->warp_kernel && !blob.empty() &&
+		    covered * 10 >= sampled_lines * 9;
+	return 0;
 }
 
 /*
@@ -299,11 +355,13 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 				s->wslice = sl;
 			}
 		}
+		s->f_nsl = s->wslice / 16;
 	}
 	if (!s->tmpl_enabled)
 		return 0;
 	std::vector<TCandidate> cands;
-	tmpl_candidates(head.data(), n, TMPL_MAX_LEAVES, cands);
+	size_t sampled_lines = 0;
+	tmpl_candidates(head.data(), n, TMPL_MAX_LEAVES, cands, &sampled_lines);
 	if (cands.empty())
 		return 0;
 	std::vector<u8> lines;
@@ -353,6 +411,8 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 	cached_free(d_res);
 	if (e != cudaSuccess)
 		return s->cuda(e, "template resolve");
+	if (s->fplan.ok && learn_ftemplates(s, cands, res, sampled_lines))
+		return s->err_code;
 	std::vector<u8> blob;
 	u32 nt = 0;
 	tmpl_build(cands, res, TMPL_RESERVE, blob, &nt);
@@ -371,6 +431,132 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 	s->tmpl_bytes = (u32)padded;
 	s->ntemplates = nt;
 	return 0;
+}
+
+template <int NSL>
+void launch_fkernel(dng_scan *s, const FScanArgs &a, u32 grid)
+{
+	scan_kernel_f<NSL><<<grid, DNG_NT, fkernel_smem<NSL>(a.tmpl_bytes,
+	    a.s1slots, a.sslots, a.nrows), s->stream>>>(a);
+}
+
+/* tally-cache sizes of the F kernel: what its buffers leave */
+template <int NSL>
+void fkernel_slots(const dng_scan *s, u32 nrows, u32 *s1, u32 *s2)
+{
+	const size_t fixed = fkernel_smem<NSL>(TMPL_RESERVE, 0, 0, nrows);
+	const size_t room = s->f_smem_max > fixed ? s->f_smem_max - fixed : 0;
+	u32 n1 = 32;
+	while (n1 < 1024 && (size_t)n1 * 2 * sizeof (SSlot1) +
+	    DNG_SSLOTS_MIN * sizeof (SSlot) <= room * 3 / 4)
+		n1 *= 2;
+	const size_t left = room - std::min(room, (size_t)n1 * sizeof (SSlot1));
+	u32 n2 = DNG_SSLOTS_MIN;
+	while (n2 * 2 <= DNG_SSLOTS_MAX && (size_t)n2 * 2 * sizeof (SSlot) <= left)
+		n2 *= 2;
+	*s1 = n1;
+	*s2 = n2;
+}
+
+/*
+ * The F path over data[start, nbytes): scan_kernel_f, then scan_miss_kernel
+ * for what it did not take (it exits at once when the list is empty).
+ */
+int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
+    unsigned long long nbytes, bool final)
+{
+	if (!s->d_miss) {
+		s->miss_cap = (u32)env_size("DNG_MISS_CAP", (size_t)4 << 20);
+		CK(s, DEV_ALLOC(s, &s->d_miss, (size_t)s->miss_cap *
+		    sizeof (MissEnt)));
+		CK(s, DEV_ALLOC(s, &s->d_miss_n, 64));
+		CK(s, cudaMemsetAsync(s->d_miss_n, 0, 64, s->stream));
+	}
+	/* the kernel wants the first valid byte inside the first 16 */
+	const unsigned long long skip = start & ~15ull;
+	data += skip;
+	start -= skip;
+	nbytes -= skip;
+	FScanArgs a;
+	a.data = data;
+	a.start = start;
+	a.nbytes = nbytes;
+	a.fplan = s->d_fplan;
+	a.plan = s->d_plan;
+	a.tmpl = s->d_ftmpl;
+	a.tmpl_bytes = s->ftmpl_bytes;
+	a.leaf_off = s->ftmpl_leaf_off;
+	a.pool_off = s->ftmpl_pool_off;
+	a.counters = s->d_counters;
+	a.tab = s->tab;
+	a.final = final ? 1 : 0;
+	a.nrows = s->fplan.nrows;
+	a.miss = s->d_miss;
+	a.miss_cap = s->miss_cap;
+	a.miss_n = s->d_miss_n;
+	const u32 nsl = s->f_nsl;
+	const unsigned long long chunk = 32ull * 16 * nsl;
+	a.nchunks = (u32)((nbytes + chunk - 1) / chunk);
+	const u32 grid = std::min<u32>((a.nchunks + DNG_NW - 1) / DNG_NW,
+	    (u32)s->sm_count);
+	/* segments: long enough to amortise the pre-lap, short enough to keep
+	 * every warp of the grid busy */
+	const u32 nwarps = grid * DNG_NW;
+	a.seg = std::max<u32>(1, std::min<u32>(DNG_F_SEG,
+	    a.nchunks / (nwarps * 4)));
+	cudaEvent_t e0 = get_event(s), e1 = get_event(s);
+	cudaEventRecord(e0, s->stream);
+	switch (nsl) {
+	case 7:
+		fkernel_slots<7>(s, a.nrows, &a.s1slots, &a.sslots);
+		launch_fkernel<7>(s, a, grid);
+		break;
+	case 9:
+		fkernel_slots<9>(s, a.nrows, &a.s1slots, &a.sslots);
+		launch_fkernel<9>(s, a, grid);
+		break;
+	case 11:
+		fkernel_slots<11>(s, a.nrows, &a.s1slots, &a.sslots);
+		launch_fkernel<11>(s, a, grid);
+		break;
+	default:
+		fkernel_slots<13>(s, a.nrows, &a.s1slots, &a.sslots);
+		launch_fkernel<13>(s, a, grid);
+		break;
+	}
+	cudaError_t le = cudaGetLastError();
+	FMissArgs ma;
+	ma.data = data;
+	ma.start = start;
+	ma.plan = s->d_plan;
+	ma.plan_bytes = s->plan_bytes;
+	ma.counters = s->d_counters;
+	ma.tab = s->tab;
+	ma.s1slots = 64;
+	ma.sslots = 1024;
+	ma.miss = s->d_miss;
+	ma.miss_n = s->d_miss_n;
+	ma.miss_cap = s->miss_cap;
+	if (le == cudaSuccess) {
+		scan_miss_kernel<<<s->sm_count * 2, DNG_MISS_NT, s->plan_bytes +
+		    ma.s1slots * sizeof (SSlot1) + ma.sslots * sizeof (SSlot),
+		    s->stream>>>(ma);
+		le = cudaGetLastError();
+	}
+	cudaMemsetAsync(s->d_miss_n, 0, sizeof (u32), s->stream);
+	cudaEventRecord(e1, s->stream);
+	if (!s->h_live && HOST_ALLOC(&s->h_live, 16 * sizeof (unsigned long long))
+	    == cudaSuccess)
+		memset(s->h_live, 0, 16 * sizeof (unsigned long long));
+	if (s->h_live)
+		cudaMemcpyAsync(s->h_live, s->d_counters,
+		    16 * sizeof (unsigned long long), cudaMemcpyDeviceToHost,
+		    s->stream);
+	s->ev_pairs.emplace_back(e0, e1);
+	s->launches++;
+	s->aux_launches++;
+	s->kernel_bytes += nbytes - start;
+	return s->cuda(le, "scan_kernel_f launch");
 }
 
 /* launch the scan kernel over data[start, nbytes) */
@@ -402,8 +588,18 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 			s->seen_long = nlong;
 		}
 		const unsigned long long dl = lines - s->learn_lines;
+		/* the F path only pays while it takes nearly every record: with
+		 * more than a few percent going through the miss list, learn
+		 * again; if that was already done, leave it to the general
+		 * kernels (whose second tier runs from shared memory) */
+		if (s->f_kernel && s->kernel_pref == 0 && dl > 200000 &&
+		    (dl - (lv[CTR_TMPL] - s->learn_tmpl)) * 16 > dl &&
+		    s->relearns >= 1)
+			s->f_kernel = false;
+		const bool fweak = s->f_kernel && s->kernel_pref == 0 &&
+		    (dl - (lv[CTR_TMPL] - s->learn_tmpl)) * 16 > dl;
 		if (s->tmpl_enabled && s->relearns < 3 && dl > 200000 &&
-		    (lv[CTR_TMPL] - s->learn_tmpl) * 2 < dl) {
+		    ((lv[CTR_TMPL] - s->learn_tmpl) * 2 < dl || fweak)) {
 			s->relearns++;
 			const bool wk = s->warp_kernel;
 			if (learn_templates(s, data, start, nbytes))
@@ -415,6 +611,8 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 			s->learn_tmpl = lv[CTR_TMPL];
 		}
 	}
+	if (s->f_kernel && s->fplan.ok)
+		return launch_fscan(s, data, start, nbytes, final);
 	ScanArgs a;
 	a.data = data;
 	a.start = start;
@@ -669,8 +867,43 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		if (const char *ev = getenv("DNG_KERNEL")) {
 			/* tuning/testing: force one kernel geometry */
 			s->kernel_pref = !strcmp(ev, "tile") ? 1 :
-			    !strcmp(ev, "warp") ? 2 : 0;
+			    !strcmp(ev, "warp") ? 2 : !strcmp(ev, "fast") ? 3 : 0;
 			s->warp_kernel = s->kernel_pref == 2;
+		}
+		/* the F path (fast.h), for the plans it models */
+		fplan_build(plan->dev, s->fplan);
+		if (getenv("DNG_FAST") && atoi(getenv("DNG_FAST")) == 0)
+			s->fplan.ok = 0;
+		if (s->kernel_pref == 3) {
+			/* forced: every eligible plan takes it, whatever the
+			 * templates cover; others choose as usual */
+			s->f_kernel = s->fplan.ok != 0;
+			if (!s->f_kernel)
+				s->kernel_pref = plan->dev.nmetrics > 1 ? 1 : 0;
+		}
+		s->f_smem_max = (u32)prop.sharedMemPerBlockOptin - 1024;
+		{
+			cudaError_t fe = cudaFuncSetAttribute(scan_kernel_f<7>,
+			    cudaFuncAttributeMaxDynamicSharedMemorySize,
+			    (int)s->f_smem_max);
+			if (fe == cudaSuccess)
+				fe = cudaFuncSetAttribute(scan_kernel_f<9>,
+				    cudaFuncAttributeMaxDynamicSharedMemorySize,
+				    (int)s->f_smem_max);
+			if (fe == cudaSuccess)
+				fe = cudaFuncSetAttribute(scan_kernel_f<11>,
+				    cudaFuncAttributeMaxDynamicSharedMemorySize,
+				    (int)s->f_smem_max);
+			if (fe == cudaSuccess)
+				fe = cudaFuncSetAttribute(scan_kernel_f<13>,
+				    cudaFuncAttributeMaxDynamicSharedMemorySize,
+				    (int)s->f_smem_max);
+			if (fe == cudaSuccess)
+				fe = cudaFuncSetAttribute(scan_miss_kernel,
+				    cudaFuncAttributeMaxDynamicSharedMemorySize,
+				    (int)s->f_smem_max);
+			if ((rc = s->cuda(fe, "cudaFuncSetAttribute")))
+				break;
 		}
 		if ((rc = s->cuda(cudaFuncSetAttribute(scan_kernel,
 		    cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -711,6 +944,15 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		if ((rc = s->cuda(DEV_ALLOC(s, &s->d_plan, sizeof (DevPlan) + 256),
 		    "cudaMalloc plan")))
 			break;
+		if (s->fplan.ok) {
+			if ((rc = s->cuda(DEV_ALLOC(s, &s->d_fplan, FPLAN_SMEM),
+			    "cudaMalloc fplan")))
+				break;
+			if ((rc = s->cuda(cudaMemcpyAsync(s->d_fplan, &s->fplan,
+			    sizeof (FPlan), cudaMemcpyHostToDevice, s->stream),
+			    "fplan upload")))
+				break;
+		}
 		/* s->plan is this scan's own copy: safe to upload from */
 		if ((rc = s->cuda(cudaMemcpyAsync(s->d_plan, &s->plan.dev,
 		    sizeof (DevPlan), cudaMemcpyHostToDevice, s->stream),
@@ -1400,6 +1642,10 @@ void dng_scan_destroy(dng_scan *s)
 	cached_free(s->h_live);
 	cached_free(s->d_plan);
 	cached_free(s->d_tmpl);
+	cached_free(s->d_fplan);
+	cached_free(s->d_ftmpl);
+	cached_free(s->d_miss);
+	cached_free(s->d_miss_n);
 	cached_free(s->tab.entries);
 	cached_free(s->tab.arena);
 	cached_free(s->tab.misc);

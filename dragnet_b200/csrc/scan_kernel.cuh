@@ -713,40 +713,33 @@ __device__ __forceinline__ bool scan_record(WinCtx &w, u32 phase, bool have,
 	return failed;
 }
 
-/* end of a kernel: shared tally cache -> global table, counters -> global */
-__device__ __forceinline__ void scan_epilogue(const ScanArgs &a,
-    const DevPlan &P, const STab &stab, const LocalCounters &C,
-    const u32 *s_mctr, u32 nlong, u32 ntmpl)
+/* end of a kernel, part 1: the CTA's tally cache -> the global table */
+__device__ __forceinline__ void flush_tally(const STab &stab, u32 s1slots,
+    u32 sslots, const GTable &tab)
 {
-	const u32 tid = threadIdx.x, lane = tid & 31;
+	const u32 tid = threadIdx.x;
 	__syncthreads();
-	for (u32 i = tid; i < a.s1slots; i += DNG_NT) {
+	for (u32 i = tid; i < s1slots; i += blockDim.x) {
 		const SSlot1 *s = &stab.s1[i];
 		if (s->tag != 0 && s->count)
-			global_add(a.tab, key_hash_words(s->key, s->klen),
+			global_add(tab, key_hash_words(s->key, s->klen),
 			    (const u8 *)s->key, s->klen,
 			    (unsigned long long)s->count);
 	}
-	for (u32 i = tid; i < a.sslots; i += DNG_NT) {
+	for (u32 i = tid; i < sslots; i += blockDim.x) {
 		const SSlot *s = &stab.s[i];
 		if (s->tag != 0 && s->gidx1 != 0 && s->gidx1 != 0xffffffffu &&
 		    s->count)
-			atomicAdd(&a.tab.entries[s->gidx1 - 1].count,
+			atomicAdd(&tab.entries[s->gidx1 - 1].count,
 			    (unsigned long long)s->count);
 	}
+}
 
-	if (P.nmetrics > 1) {
-		for (u32 k = 0; k < (u32)(P.nmetrics - 1) * MCTR_PER; k++) {
-			u32 v = s_mctr[k];
-			for (int d = 16; d > 0; d >>= 1)
-				v += __shfl_xor_sync(0xffffffffu, v, d);
-			if (lane == 0 && v)
-				atomicAdd(&a.counters[NCTR + k],
-				    (unsigned long long)v);
-		}
-	}
-
-	/* counters: warp reduce, one atomic per warp per counter */
+/* part 2: per-thread counters: warp reduce, one atomic per warp per counter */
+__device__ __forceinline__ void flush_counters(unsigned long long *counters,
+    const LocalCounters &C, u32 nlong, u32 ntmpl)
+{
+	const u32 lane = threadIdx.x & 31;
 	u32 vals[NCTR];
 	for (int k = 0; k < NCTR; k++)
 		vals[k] = 0;
@@ -772,8 +765,29 @@ __device__ __forceinline__ void scan_epilogue(const ScanArgs &a,
 		for (int d = 16; d > 0; d >>= 1)
 			v += __shfl_xor_sync(0xffffffffu, v, d);
 		if (lane == 0 && v)
-			atomicAdd(&a.counters[k], (unsigned long long)v);
+			atomicAdd(&counters[k], (unsigned long long)v);
 	}
+}
+
+/* end of a kernel: shared tally cache -> global table, counters -> global */
+__device__ __forceinline__ void scan_epilogue(const ScanArgs &a,
+    const DevPlan &P, const STab &stab, const LocalCounters &C,
+    const u32 *s_mctr, u32 nlong, u32 ntmpl)
+{
+	const u32 lane = threadIdx.x & 31;
+	flush_tally(stab, a.s1slots, a.sslots, a.tab);
+
+	if (P.nmetrics > 1) {
+		for (u32 k = 0; k < (u32)(P.nmetrics - 1) * MCTR_PER; k++) {
+			u32 v = s_mctr[k];
+			for (int d = 16; d > 0; d >>= 1)
+				v += __shfl_xor_sync(0xffffffffu, v, d);
+			if (lane == 0 && v)
+				atomicAdd(&a.counters[NCTR + k],
+				    (unsigned long long)v);
+		}
+	}
+	flush_counters(a.counters, C, nlong, ntmpl);
 }
 
 /*

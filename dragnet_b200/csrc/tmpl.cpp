@@ -118,9 +118,11 @@ bool tmpl_skeletonize(const u8 *s, u32 n, std::vector<TSeg> &out)
 }
 
 void tmpl_candidates(const u8 *data, size_t len, size_t maxk,
-    std::vector<TCandidate> &out)
+    std::vector<TCandidate> &out, size_t *nlines_out)
 {
 	out.clear();
+	if (nlines_out)
+		*nlines_out = 0;
 	/* count shapes by a hash of their skeleton; only the first line of each
 	 * distinct shape is broken into segments */
 	std::map<u64, size_t> seen;
@@ -156,6 +158,8 @@ void tmpl_candidates(const u8 *data, size_t len, size_t maxk,
 	    [](const TCandidate &a, const TCandidate &b) {
 		    return a.count > b.count;
 	    });
+	if (nlines_out)
+		*nlines_out = nlines;
 	/* shapes seen in under 0.5% of the lines are not worth a trie branch */
 	size_t keep = 0;
 	while (keep < out.size() && keep < maxk &&
@@ -295,8 +299,9 @@ struct Trie {
 	std::vector<BNode> nodes;	/* nodes[0] = virtual root */
 	std::vector<u32> leaf_mask;
 	size_t pool;
+	bool compact;		/* literals as plain words (the F path) */
 
-	Trie() : pool(0) {
+	explicit Trie(bool compact_ = false) : pool(0), compact(compact_) {
 		BNode r;
 		r.kind = r.cap = r.poscap = 0;
 		r.posoff = 0;
@@ -323,7 +328,8 @@ struct Trie {
 				hit = (int)nodes.size();
 				nodes.push_back(b);
 				nodes[cur].kids.push_back(hit);
-				pool += (g.lit.size() + 7) / 8 * 16;
+				pool += compact ? (g.lit.size() + 3) / 4 * 4 + 12 :
+				    (g.lit.size() + 7) / 8 * 16;
 			} else {
 				BNode &b = nodes[hit];
 				if (g.cap) {
@@ -474,28 +480,37 @@ bool build_trie(const std::vector<PTmpl> &ts, Trie &tr, size_t max_bytes)
 
 void tmpl_build(const std::vector<TCandidate> &cands,
     const std::vector<TResolved> &res, size_t max_bytes, std::vector<u8> &blob,
-    u32 *ntemplates)
+    u32 *ntemplates, bool compact, std::vector<u8> *accepted)
 {
 	blob.clear();
 	if (ntemplates)
 		*ntemplates = 0;
+	if (accepted)
+		accepted->assign(cands.size(), 0);
 	std::vector<PTmpl> acc;
+	std::vector<size_t> acc_idx;
 	for (size_t i = 0; i < cands.size() && i < res.size(); i++) {
 		PTmpl t;
 		if (!plan_template(cands[i], res[i], t))
 			continue;
 		acc.push_back(t);
-		Trie probe;
-		if (!build_trie(acc, probe, max_bytes))
+		acc_idx.push_back(i);
+		Trie probe(compact);
+		if (!build_trie(acc, probe, max_bytes)) {
 			acc.pop_back();
+			acc_idx.pop_back();
+		}
 	}
 	if (acc.empty())
 		return;
-	Trie tr;
+	Trie tr(compact);
 	if (!build_trie(acc, tr, max_bytes))
 		return;
 	if (ntemplates)
 		*ntemplates = (u32)acc.size();
+	if (accepted)
+		for (size_t i : acc_idx)
+			(*accepted)[i] = 1;
 
 	/* number the nodes: the children of one node are consecutive and
 	 * chained through `alt`; the root's first child is node 0 */
@@ -557,7 +572,8 @@ void tmpl_build(const std::vector<TCandidate> &cands,
 					mk |= 0xffu << (8 * x);
 				}
 				pool.append((const char *)&v, 4);
-				pool.append((const char *)&mk, 4);
+				if (!compact)
+					pool.append((const char *)&mk, 4);
 			}
 			pool.append((16 - pool.size() % 16) % 16, '\0');
 			o.kind = b.kind;

@@ -103,15 +103,19 @@ struct TCandidate {
 bool tmpl_skeletonize(const u8 *s, u32 n, std::vector<TSeg> &out);
 
 /* distinct skeletons of the complete lines in data[0, len), most frequent
- * first, at most maxk */
+ * first, at most maxk; *nlines = the lines looked at */
 void tmpl_candidates(const u8 *data, size_t len, size_t maxk,
-    std::vector<TCandidate> &out);
+    std::vector<TCandidate> &out, size_t *nlines = nullptr);
 
 /* the trie blob (at most max_bytes) for the candidates that resolved cleanly,
- * most frequent first; empty if none did.  *ntemplates = how many it holds. */
+ * most frequent first; empty if none did.  *ntemplates = how many it holds.
+ * compact: literals as plain little-endian words, zero padded, instead of
+ * { value, mask } pairs (the F path, fast.cuh fmatch).  accepted[i] = 1 for
+ * the candidates the blob holds. */
 void tmpl_build(const std::vector<TCandidate> &cands,
     const std::vector<TResolved> &res, size_t max_bytes, std::vector<u8> &blob,
-    u32 *ntemplates);
+    u32 *ntemplates, bool compact = false,
+    std::vector<u8> *accepted = nullptr);
 
 } /* namespace dng */
 

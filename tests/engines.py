@@ -38,10 +38,10 @@ def build_hostcheck():
     exe = os.path.join(HOSTCHECK_DIR, 'hostcheck')
     srcs = [os.path.join(HOSTCHECK_DIR, 'hostcheck.cpp'),
             os.path.join(CSRC, 'plan.cpp'), os.path.join(CSRC, 'result.cpp'),
-            os.path.join(CSRC, 'tmpl.cpp')]
+            os.path.join(CSRC, 'tmpl.cpp'), os.path.join(CSRC, 'fast.cpp')]
     deps = srcs + [os.path.join(CSRC, n) for n in
                    ('record.cuh', 'jsnum.cuh', 'jsdate.cuh', 'plan.h',
-                    'result.h', 'tmpl.h', 'tmpl.cuh')]
+                    'result.h', 'tmpl.h', 'tmpl.cuh', 'fast.h', 'fast.cuh')]
     if not os.path.exists(exe) or \
             os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(['g++', '-std=c++17', '-O1', '-g', '-o', exe] +

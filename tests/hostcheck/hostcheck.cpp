@@ -19,6 +19,7 @@
 
 #include "../../dragnet_b200/csrc/record.cuh"
 #include "../../dragnet_b200/csrc/tmpl.cuh"
+#include "../../dragnet_b200/csrc/fast.cuh"
 #include "../../dragnet_b200/csrc/result.h"
 #include "../../include/dragnet_gpu.h"
 
@@ -79,6 +80,34 @@ int main(int argc, char **argv)
 			    blob.empty() ? 0 : ((THdr *)blob.data())->nnodes,
 			    blob.empty() ? 0 : ((THdr *)blob.data())->nleaves);
 	}
+	/* DNG_HOSTCHECK_F: the F path (fast.cuh) in front of everything else:
+	 * its own (path indexed, compact) templates, its stages and its
+	 * piece-wise key functions; misses fall through to the code below */
+	static FPlan FP;
+	std::vector<u8> fblob;
+	unsigned long nf_match = 0, nf_miss = 0;
+	std::map<std::string, u32> fhashes;
+	if (getenv("DNG_HOSTCHECK_F") != nullptr) {
+		fplan_build(plan.dev, FP);
+		if (FP.ok) {
+			std::vector<TCandidate> cands;
+			tmpl_candidates((const u8 *)data.data(),
+			    std::min<size_t>(data.size(), TMPL_SAMPLE_BYTES),
+			    TMPL_MAX_LEAVES, cands);
+			std::vector<TResolved> res(cands.size());
+			for (size_t i = 0; i < cands.size(); i++) {
+				static RecState TR;
+				TResolved r0;
+				parse_record((const u8 *)cands[i].sample.data(),
+				    (u32)cands[i].sample.size(), plan.dev, TR);
+				r0.flags = TR.flags;
+				r0.set_mask = TR.set_mask;
+				memcpy(r0.slots, TR.slots, sizeof (TR.slots));
+				fplan_resolve(plan.dev, r0, res[i]);
+			}
+			tmpl_build(cands, res, 60000, fblob, nullptr, true);
+		}
+	}
 	static LocalCounters MCs[MAX_METRICS];
 	memset(MCs, 0, sizeof (MCs));
 	std::map<std::string, uint64_t> table;
@@ -92,6 +121,74 @@ int main(int argc, char **argv)
 		const u8 *rec = (const u8 *)data.data() + pos;
 		C.lines++;
 		bool done = false;
+		if (!fblob.empty() && nl != std::string::npos && len <= 4095) {
+			FastHostMem fm;
+			fm.rec = rec;
+			fm.len = len;
+			fm.blob = fblob.data();
+			u32 defmask = 0;
+			double s0 = 0, s1 = 0;
+			u32 fo = FO_MISS, h = 0, klen = 0, slow = 0;
+			if (fmatch(fm, len, true, defmask))
+				fo = fstage(fm, FP, defmask, s0, s1);
+			if (fo == FO_AGGR &&
+			    (!fprep(fm, FP, defmask, s0, s1, slow) ||
+			    !fkey_hash(fm, FP, defmask, h, klen)))
+				fo = FO_MISS;
+			if (fo != FO_MISS) {
+				nf_match++;
+				switch (fo) {
+				case FO_DS_FILTERED: C.ds_filtered++; break;
+				case FO_DS_FAILED: C.ds_failedeval++; break;
+				case FO_USER_FILTERED: C.user_filtered++; break;
+				case FO_USER_FAILED: C.user_failedeval++; break;
+				case FO_SYNTH_UNDEF: C.synth_undef++; break;
+				case FO_SYNTH_BADDATE: C.synth_baddate++; break;
+				case FO_TIME_FILTERED: C.time_filtered++; break;
+				case FO_TIME_FAILED: C.time_failedeval++; break;
+				default: {
+					memset(kbuf, 0xee, F_MAXKEY + 8);
+					fkey_write(fm, FP, defmask, kbuf);
+					std::string key((char *)kbuf, klen);
+					/* the piece-wise functions agree with the
+					 * key they describe */
+					FastHostKey hk;
+					hk.key = kbuf;
+					hk.len = klen;
+					if (!fkey_equal(fm, FP, defmask, hk)) {
+						fprintf(stderr, "fkey_equal: own key\n");
+						return 3;
+					}
+					auto it = fhashes.find(key);
+					if (it != fhashes.end() && it->second != h) {
+						fprintf(stderr, "fkey_hash: unstable\n");
+						return 3;
+					}
+					for (auto &kv : fhashes) {
+						if (kv.first == key ||
+						    kv.first.size() != key.size())
+							continue;
+						FastHostKey ok_;
+						ok_.key = (const u8 *)kv.first.data();
+						ok_.len = (u32)kv.first.size();
+						if (fkey_equal(fm, FP, defmask, ok_)) {
+							fprintf(stderr, "fkey_equal: "
+							    "other key\n");
+							return 3;
+						}
+					}
+					fhashes[key] = h;
+					table[key] += 1;
+					C.aggr++;
+					if (slow)
+						C.slow++;
+				}
+				}
+				pos = end + 1;
+				continue;
+			}
+			nf_miss++;
+		}
 		if (!blob.empty() && nl != std::string::npos) {
 			TmplHostMem m;
 			m.rec = rec;
@@ -191,6 +288,7 @@ int main(int argc, char **argv)
 		    M.time_failedeval, M.aggr);
 		C.unsupported += M.unsupported;
 	}
-	printf("],\"nfast\":%lu,\"ntmpl\":%lu}\n", nfast, ntmpl);
+	printf("],\"nfast\":%lu,\"ntmpl\":%lu,\"nfmatch\":%lu,\"nfmiss\":%lu}\n",
+	    nfast, ntmpl, nf_match, nf_miss);
 	return 0;
 }

@@ -16,10 +16,12 @@ from golden_harness import check_section  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['auto', 'tile', 'warp'], autouse=True)
+@pytest.fixture(params=['auto', 'tile', 'warp', 'fast'], autouse=True)
 def kernel_geometry(request, monkeypatch):
-    """Every case under both kernel geometries (CTA-wide tiles, per-warp
-    chunks) and under the library's own choice between them."""
+    """Every case under the general kernels' two geometries (CTA-wide tiles,
+    per-warp chunks), under the F path forced on (scan_kernel_f + the miss
+    kernel, whatever the templates cover) and under the library's own choice
+    between them."""
     monkeypatch.delenv('DNG_KERNEL', raising=False)
     if request.param != 'auto':
         monkeypatch.setenv('DNG_KERNEL', request.param)

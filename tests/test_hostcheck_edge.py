@@ -8,13 +8,18 @@ import sys
 import pytest
 
 
-@pytest.fixture(params=['general', 'fast', 'tmpl'], autouse=True)
+@pytest.fixture(params=['general', 'fast', 'tmpl', 'fpath'], autouse=True)
 def parser_mode(request, monkeypatch):
     """Run every case with the general parser only, with the lock-step fast
     automaton (+ fallback), and with record templates learned from the input
-    in front of both -- the three tiers the kernel uses."""
+    in front of both -- the three tiers the general kernels use -- and with the
+    F path (fast.cuh: path-indexed templates, lean stages, piece-wise keys) in
+    front of all of them, as scan_kernel_f does."""
     monkeypatch.delenv('DNG_HOSTCHECK_FAST', raising=False)
     monkeypatch.delenv('DNG_HOSTCHECK_TMPL', raising=False)
+    monkeypatch.delenv('DNG_HOSTCHECK_F', raising=False)
+    if request.param == 'fpath':
+        monkeypatch.setenv('DNG_HOSTCHECK_F', '1')
     if request.param in ('fast', 'tmpl'):
         monkeypatch.setenv('DNG_HOSTCHECK_FAST', '1')
     if request.param == 'tmpl':

@@ -19,7 +19,9 @@ for cub in glob.glob(os.path.join(d, 'api*.cubin')):
         m = re.search(r'//## File "([^"]+)", line (\d+)', l)
         if m:
             fl, ln = m.group(1).split('/')[-1], int(m.group(2))
-        if not (fn and (os.environ.get('NCU_FN', 'scan_kernel_w') + 'ENS_8ScanArgs') in fn):
+        want = os.environ.get('NCU_FN', 'scan_kernel_w')
+        if not (fn and ((want + 'ENS_8ScanArgs') in fn or
+                        ('fILi' in want and want in fn))):
             continue
         m = re.match(r'^\s*/\*([0-9a-f]{4,})\*/\s+(\S.*?);', l)
         if m:
