@@ -31,6 +31,7 @@
 #include "result.h"
 #include "scan_kernel.cuh"
 #include "fast_kernel.cuh"
+#include "jit.h"
 #include "gen.cuh"
 
 using namespace dng;
@@ -197,7 +198,12 @@ struct dng_scan {
 	u32 ftmpl_bytes = 0, nftemplates = 0, ftmpl_leaf_off = 0, ftmpl_pool_off = 0;
 	bool f_kernel = false;
 	u32 f_nsl = 13;			/* 16-byte units per lane slice */
+	double mean_line = 224;		/* of the sample the templates came from */
 	u32 f_smem_max = 0;		/* dynamic shared memory a CTA may ask for */
+	/* run-time compiled matcher (jit.h): 0 off, 1 in the background, 2 wait */
+	int jit_mode = 1;
+	std::shared_ptr<JitKernels> jit;
+	uint64_t jit_launches = 0;
 	MissEnt *d_miss = nullptr;
 	u32 *d_miss_n = nullptr;
 	u32 miss_cap = 0;
@@ -291,9 +297,14 @@ int learn_ftemplates(dng_scan *s, const std::vector<TCandidate> &cands,
 		s->ftmpl_bytes = (u32)padded;
 		s->nftemplates = nt;
 	}
+	s->jit.reset();
+	if (s->jit_mode && !blob.empty())
+		s->jit = jit_request(jit_source(blob.data(), blob.size()),
+		    s->device, (int)s->f_smem_max, s->jit_mode == 2);
 	if (s->kernel_pref == 0)
 		s->f_kernel = s->warp_kernel && !blob.empty() &&
-		    covered * 10 >= sampled_lines * 9;
+		    covered * 10 >= sampled_lines * 9 &&
+		    s->mean_line * DNG_F_NLCAP >= 32.0 * 16 * s->f_nsl * 1.5;
 	return 0;
 }
 
@@ -345,6 +356,7 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 		for (size_t i = 0; i < n; i++)
 			nl += head[i] == '\n';
 		double mean = nl ? (double)n / (double)nl : 224.0;
+		s->mean_line = mean;
 		double best = -1;
 		for (u32 sl = 112; sl <= DNG_W_SLICE_MAX; sl += 32) {
 			double recs = 32.0 * sl / mean;
@@ -506,25 +518,48 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 	    a.nchunks / (nwarps * 4)));
 	cudaEvent_t e0 = get_event(s), e1 = get_event(s);
 	cudaEventRecord(e0, s->stream);
+	/* the matcher compiled for these templates, once it is there */
+	const bool jit = s->jit && s->jit->state.load() == 1 && s->ftmpl_bytes;
+	size_t smem = 0;
+	int ki = 3;
 	switch (nsl) {
 	case 7:
 		fkernel_slots<7>(s, a.nrows, &a.s1slots, &a.sslots);
-		launch_fkernel<7>(s, a, grid);
+		smem = fkernel_smem<7>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
+		ki = 0;
+		if (!jit)
+			launch_fkernel<7>(s, a, grid);
 		break;
 	case 9:
 		fkernel_slots<9>(s, a.nrows, &a.s1slots, &a.sslots);
-		launch_fkernel<9>(s, a, grid);
+		smem = fkernel_smem<9>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
+		ki = 1;
+		if (!jit)
+			launch_fkernel<9>(s, a, grid);
 		break;
 	case 11:
 		fkernel_slots<11>(s, a.nrows, &a.s1slots, &a.sslots);
-		launch_fkernel<11>(s, a, grid);
+		smem = fkernel_smem<11>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
+		ki = 2;
+		if (!jit)
+			launch_fkernel<11>(s, a, grid);
 		break;
 	default:
 		fkernel_slots<13>(s, a.nrows, &a.s1slots, &a.sslots);
-		launch_fkernel<13>(s, a, grid);
+		smem = fkernel_smem<13>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
+		if (!jit)
+			launch_fkernel<13>(s, a, grid);
 		break;
 	}
-	cudaError_t le = cudaGetLastError();
+	cudaError_t le = cudaSuccess;
+	if (jit) {
+		void *args[] = { &a };
+		le = cudaLaunchKernel((const void *)s->jit->kern[ki], dim3(grid),
+		    dim3(DNG_NT), args, smem, s->stream);
+		s->jit_launches++;
+	}
+	if (le == cudaSuccess)
+		le = cudaGetLastError();
 	FMissArgs ma;
 	ma.data = data;
 	ma.start = start;
@@ -874,6 +909,9 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		fplan_build(plan->dev, s->fplan);
 		if (getenv("DNG_FAST") && atoi(getenv("DNG_FAST")) == 0)
 			s->fplan.ok = 0;
+		if (const char *ev = getenv("DNG_JIT"))
+			s->jit_mode = !strcmp(ev, "sync") || !strcmp(ev, "wait") ? 2 :
+			    (!strcmp(ev, "0") || !strcmp(ev, "off")) ? 0 : 1;
 		if (s->kernel_pref == 3) {
 			/* forced: every eligible plan takes it, whatever the
 			 * templates cover; others choose as usual */
@@ -1570,7 +1608,25 @@ int dng_scan_kernel_kind(const dng_scan *s)
 {
 	if (!s)
 		return DNG_EINVAL;
-	return s->warp_kernel ? 1 : 0;
+	return s->f_kernel && s->fplan.ok ? 2 : s->warp_kernel ? 1 : 0;
+}
+
+int dng_scan_jit_stats(dng_scan *s, int *state, uint64_t *launches,
+    double *compile_ms, double *link_ms, char *err, size_t errlen)
+{
+	if (!s)
+		return DNG_EINVAL;
+	const int st = s->jit ? s->jit->state.load() : 0;
+	if (state)
+		*state = st;
+	if (launches)
+		*launches = s->jit_launches;
+	if (compile_ms)
+		*compile_ms = st ? s->jit->compile_ms : 0;
+	if (link_ms)
+		*link_ms = st ? s->jit->link_ms : 0;
+	set_err(err, errlen, "%s", st == 2 ? s->jit->err.c_str() : "");
+	return DNG_OK;
 }
 
 int dng_scan_kernel_stats(dng_scan *s, double *kernel_ms, uint64_t *launches,

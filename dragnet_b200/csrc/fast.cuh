@@ -24,21 +24,12 @@
 
 namespace dng {
 
+#include "fscan.cuh"		/* (includes nothing: lives in this namespace) */
+
 DNG_HD u32 fcap_off(u32 c) { return c & 0xfff; }
 DNG_HD u32 fcap_len(u32 c) { return (c >> 12) & 0xfff; }
 DNG_HD u32 fcap_type(u32 c) { return (c >> 24) & 7; }
 DNG_HD u32 fcap_flag(u32 c) { return c >> 27; }
-
-/* 0x80 in (at least) the lowest byte of w that ends a plain run of string
- * body: '"', '\\' or a control byte */
-DNG_HD u32 fstr_stop(u32 w)
-{
-	const u32 x1 = w ^ 0x22222222u;
-	const u32 x2 = w ^ 0x5c5c5c5cu;
-	const u32 x3 = w & 0xe0e0e0e0u;
-	return (((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) |
-	    ((x3 - 0x01010101u) & ~x3)) & 0x80808080u;
-}
 
 /*
  * Match one record against the F trie.  Same trie format and the same walk as
@@ -79,111 +70,10 @@ DNG_HD bool fmatch(M &m, u32 len, bool active, u32 &defmask)
 			u32 q = p + L;
 			u32 val = 0;
 			const u32 kind = nd.z & 0xff;
-			if (ok && kind == TK_STR) {
-				/* first '"', '\\' or control byte from q on; an escape
-				 * is checked and stepped over, and the scan goes on */
-				u32 e = q, esc = 0;
-				for (;;) {
-					typename M::Cur c = m.cursor(e);
-					u32 hit, w;
-					/* eight bytes a round */
-#pragma unroll 1
-					for (;;) {
-						w = c.next();
-						hit = fstr_stop(w);
-						const u32 w2 = c.next();
-						const u32 hit2 = fstr_stop(w2);
-						if (hit)
-							break;
-						e += 4;
-						w = w2;
-						hit = hit2;
-						if (hit)
-							break;
-						e += 4;
-					}
-					const u32 b = low_flag_byte(hit);
-					e += b;
-					const u32 stop = (w >> (8 * b)) & 0xff;
-					if (stop != '\\') {
-						ok = stop == '"';
-						break;
-					}
-					const u32 c1 = m.byte(e + 1);
-					if (c1 == 'u') {
-						ok = is_hex(m.byte(e + 2)) &&
-						    is_hex(m.byte(e + 3)) &&
-						    is_hex(m.byte(e + 4)) &&
-						    is_hex(m.byte(e + 5));
-						e += 6;
-					} else {
-						ok = c1 == '"' || c1 == '\\' || c1 == '/' ||
-						    c1 == 'b' || c1 == 'f' || c1 == 'n' ||
-						    c1 == 'r' || c1 == 't';
-						e += 2;
-					}
-					esc = 1;
-					if (!ok)
-						break;
-				}
-				val = DNG_FCAP(T_STR, q, e - q, esc);
-				q = e;
-			} else if (ok && kind == TK_BARE) {
-				typename M::Cur c = m.cursor(q);
-				u32 w = c.next();
-				const u32 c0 = w & 0xff;
-				if (c0 == 't') {
-					ok = w == 0x65757274u;
-					val = DNG_FCAP(T_TRUE, q, 4, 0);
-					q += 4;
-				} else if (c0 == 'n') {
-					ok = w == 0x6c6c756eu;
-					val = DNG_FCAP(T_NULL, q, 4, 0);
-					q += 4;
-				} else if (c0 == 'f') {
-					ok = w == 0x736c6166u && (c.next() & 0xff) == 'e';
-					val = DNG_FCAP(T_FALSE, q, 5, 0);
-					q += 5;
-				} else {
-					/* -?(0|[1-9][0-9]*) word-wise; a fraction or an
-					 * exponent continues byte-wise */
-					const u32 neg = c0 == '-';
-					if (neg)
-						w = (w >> 8) | (m.byte(q + 4) << 24);
-					const u32 d0 = w & 0xff;
-					u32 i = q + neg, nd_ = 0, mk;
-					while ((mk = nondigit_mask(w)) == 0) {
-						nd_ += 4;
-						w = neg ? m.word(i + nd_) : c.next();
-					}
-					nd_ += low_flag_byte(mk);
-					ok = nd_ > 0 && !(d0 == '0' && nd_ > 1);
-					i += nd_;
-					u32 simple = 1;
-					if (nd_ > 15 || (neg && nd_ == 1 && d0 == '0'))
-						simple = 0;
-					u32 ch = (w >> (8 * low_flag_byte(mk))) & 0xff;
-					if (ok && (ch == '.' || (ch | 0x20) == 'e')) {
-						simple = 0;
-						if (ch == '.') {
-							ch = m.byte(++i);
-							ok = tm_isdigit(ch);
-							while (tm_isdigit(ch))
-								ch = m.byte(++i);
-						}
-						if (ok && (ch | 0x20) == 'e') {
-							ch = m.byte(++i);
-							if (ch == '+' || ch == '-')
-								ch = m.byte(++i);
-							ok = tm_isdigit(ch);
-							while (tm_isdigit(ch))
-								ch = m.byte(++i);
-						}
-					}
-					val = DNG_FCAP(T_NUM, q, i - q, simple);
-					q = i;
-				}
-			}
+			if (ok && kind == TK_STR)
+				ok = fscan_str(m, q, val);
+			else if (ok && kind == TK_BARE)
+				ok = fscan_bare(m, q, val);
 			if (!ok) {
 				const u32 alt = nd.y >> 16;
 				active = alt != TN_NOALT;

@@ -38,6 +38,7 @@ namespace dng {
 enum : int {
 	F_MAXPATHS = 8, F_MAXCODE = 16, F_MAXCOLS = 6, F_MAXSYN = 2,
 	F_POOL = 512, F_MAXKEY = 256,
+	F_MAXLINE = 4095,		/* longest line the F path matches */
 	F_MAXROWS = F_MAXPATHS + 2 * F_MAXCOLS	/* capture rows: paths, ordinals */
 };
 

@@ -261,9 +261,18 @@ __device__ __forceinline__ void fmiss_put(const FScanArgs &a, const STab &stab,
 	}
 }
 
-template <int NSL>
-__global__ void __launch_bounds__(DNG_NT, 1)
-scan_kernel_f(const FScanArgs a)
+/*
+ * The matcher the run-time compiler generates for one scan's templates
+ * (jit.cpp): fmatch() with the trie turned into straight-line code, literals as
+ * immediates.  Returns 0, or 1 | defmask << 1.  Only the relocatable build of
+ * this file (fast_jit.cu) calls it; it is resolved when that build is linked
+ * with the generated code.
+ */
+extern "C" __device__ unsigned dng_jmatch(unsigned ra, unsigned len,
+    unsigned active, unsigned caps);
+
+template <int NSL, bool JIT>
+__device__ __forceinline__ void fscan_body(const FScanArgs &a)
 {
 	typedef FWarpSmem<NSL> WS;
 	constexpr u32 CHUNK = WS::CHUNK, SLICE = 16 * NSL, D0 = DNG_F_PRE;
@@ -412,50 +421,41 @@ scan_kernel_f(const FScanArgs a)
 			}
 
 			/* ---- newline index ---- */
-			u32 cnt = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
-			{
-				/* bit j of hot: 16-byte unit j of the slice holds a
-				 * newline (the test has no false negatives; what it
-				 * flags is looked at exactly below) */
-				const u32 c0 = D0 + lane * SLICE;
-				u32 hot = 0;
+			/*
+			 * Bit j of hot: 16-byte unit j of the lane's slice holds a
+			 * newline (a SWAR test with no false negatives); the units
+			 * it flags are then looked at exactly, twice: to count, and
+			 * -- once a shuffle scan has ordered the lanes -- to write
+			 * the positions.
+			 */
+			const u32 c0 = D0 + lane * SLICE;
+			u32 hot = 0, cnt = 0;
 #pragma unroll
-				for (u32 j = 0; j < (u32)NSL; j++) {
-					const uint4 v = lds128(sb + c0 + 16 * j);
-					const u32 x0 = v.x ^ 0x0a0a0a0au;
-					const u32 x1 = v.y ^ 0x0a0a0a0au;
-					const u32 x2 = v.z ^ 0x0a0a0a0au;
-					const u32 x3 = v.w ^ 0x0a0a0a0au;
-					const u32 t = (((x0 - 0x01010101u) & ~x0) |
-					    ((x1 - 0x01010101u) & ~x1) |
-					    ((x2 - 0x01010101u) & ~x2) |
-					    ((x3 - 0x01010101u) & ~x3)) & 0x80808080u;
-					if (t)
-						hot |= 1u << j;
-				}
+			for (u32 j = 0; j < (u32)NSL; j++) {
+				const uint4 v = lds128(sb + c0 + 16 * j);
+				const u32 x0 = v.x ^ 0x0a0a0a0au;
+				const u32 x1 = v.y ^ 0x0a0a0a0au;
+				const u32 x2 = v.z ^ 0x0a0a0a0au;
+				const u32 x3 = v.w ^ 0x0a0a0a0au;
+				const u32 t = (((x0 - 0x01010101u) & ~x0) |
+				    ((x1 - 0x01010101u) & ~x1) |
+				    ((x2 - 0x01010101u) & ~x2) |
+				    ((x3 - 0x01010101u) & ~x3)) & 0x80808080u;
+				if (t)
+					hot |= 1u << j;
+			}
 #pragma unroll 1
-				for (; hot; hot &= hot - 1) {
-					const u32 p = c0 + 16 * (__ffs(hot) - 1);
-#pragma unroll 1
-					for (u32 q = 0; q < 4; q++) {
-						u32 mk = nl_mask(lds32(sb + p + 4 * q));
-#pragma unroll 1
-						for (; mk; mk &= mk - 1) {
-							const u32 pos = p + 4 * q +
-							    ((__ffs(mk) - 1) >> 3);
-							if (pos < lo || pos >= hi)
-								continue;
-							if (cnt == 0)
-								e1 = pos;
-							else if (cnt == 1)
-								e2 = pos;
-							else if (cnt == 2)
-								e3 = pos;
-							else if (cnt == 3)
-								e4 = pos;
-							cnt++;
-						}
-					}
+			for (u32 hm = hot; hm; hm &= hm - 1) {
+				const u32 p = c0 + 16 * (__ffs(hm) - 1);
+				const uint4 v = lds128(sb + p);
+				if (p >= lo && p + 16 <= hi) {
+					cnt += __popc(nl_mask(v.x)) + __popc(nl_mask(v.y)) +
+					    __popc(nl_mask(v.z)) + __popc(nl_mask(v.w));
+				} else {
+					/* the ends of the input: byte by byte */
+					for (u32 x = 0; x < 16; x++)
+						cnt += p + x >= lo && p + x < hi &&
+						    lds8(sb + p + x) == '\n';
 				}
 			}
 			/* an unterminated final line ends at a virtual newline:
@@ -474,8 +474,7 @@ scan_kernel_f(const FScanArgs a)
 			}
 			const u32 mybase = incl - cnt;
 			const u32 total = __shfl_sync(0xffffffffu, incl, 31);
-			const bool dense = total > DNG_F_NLCAP ||
-			    __any_sync(0xffffffffu, cnt > 4);
+			const bool dense = total > DNG_F_NLCAP;
 			if (dense) {
 				/*
 				 * Degenerate input (lines of a few bytes): one lane
@@ -505,14 +504,25 @@ scan_kernel_f(const FScanArgs a)
 				if (last >= 0)
 					beg0 = last + 1;
 			} else if (total) {
-				if (cnt > 0)
-					nlpos[mybase] = (unsigned short)e1;
-				if (cnt > 1)
-					nlpos[mybase + 1] = (unsigned short)e2;
-				if (cnt > 2)
-					nlpos[mybase + 2] = (unsigned short)e3;
-				if (cnt > 3)
-					nlpos[mybase + 3] = (unsigned short)e4;
+				{
+					u32 idx = mybase;
+#pragma unroll 1
+					for (u32 hm = hot; hm; hm &= hm - 1) {
+						const u32 p = c0 + 16 * (__ffs(hm) - 1);
+#pragma unroll 1
+						for (u32 q = 0; q < 4; q++) {
+							u32 mk = nl_mask(lds32(sb + p + 4 * q));
+#pragma unroll 1
+							for (; mk; mk &= mk - 1) {
+								const u32 pos = p + 4 * q +
+								    ((__ffs(mk) - 1) >> 3);
+								if (pos >= lo && pos < hi)
+									nlpos[idx++] =
+									    (unsigned short)pos;
+							}
+						}
+					}
+				}
 				__syncwarp();
 
 				for (u32 rb = 0; rb < total; rb += 32) {
@@ -524,12 +534,24 @@ scan_kernel_f(const FScanArgs a)
 						end = nlpos[r];
 						beg = r ? (int)nlpos[r - 1] + 1 : beg0;
 					}
-					const bool inbuf = have && beg >= 0;
+					/* (captures carry 12-bit offsets and lengths) */
+					const bool inbuf = have && beg >= 0 &&
+					    end - (u32)beg <= F_MAXLINE;
 					const u32 len = inbuf ? end - (u32)beg : 0;
 					m.ra = sb + (inbuf ? (u32)beg : 0);
 					u32 defmask = 0;
 					u32 fo = FO_MISS;
-					if (use_tmpl && fmatch(m, len, inbuf, defmask)) {
+					bool matched;
+					if (JIT) {
+						const u32 r_ = dng_jmatch(m.ra, len, inbuf,
+						    m.caps);
+						matched = r_ & 1;
+						defmask = r_ >> 1;
+					} else {
+						matched = use_tmpl &&
+						    fmatch(m, len, inbuf, defmask);
+					}
+					if (matched) {
 						double s0, s1;
 						fo = fstage(m, F, defmask, s0, s1);
 						u32 h = 0, klen = 0, slow = 0;
@@ -620,6 +642,13 @@ scan_kernel_f(const FScanArgs a)
 		if (ctr >= 0)
 			atomicAdd(&a.counters[ctr], (unsigned long long)s_drop[tid]);
 	}
+}
+
+template <int NSL>
+__global__ void __launch_bounds__(DNG_NT, 1)
+scan_kernel_f(const FScanArgs a)
+{
+	fscan_body<NSL, false>(a);
 }
 
 /* ---- the records the F path did not take ------------------------------------ */

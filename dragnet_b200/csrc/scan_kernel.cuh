@@ -62,6 +62,7 @@ namespace dng {
 #define DNG_FASTMAX 16384		/* longest line the lock-step automaton takes */
 #define DNG_SLACK 1024			/* readable bytes past the staged window */
 #define DNG_MAXREC (1u << 24)		/* longest line handled */
+#define DNG_NW (DNG_NT / 32)		/* warps per CTA */
 
 enum { NCTR = 24, MCTR_PER = 8 };	/* + (MAX_METRICS-1) x MCTR_PER for fan-out */
 enum {
@@ -819,6 +820,7 @@ __device__ __noinline__ u32 slice_newlines(u32 sbase, u32 c0, u32 c1, u32 lower)
 	return cnt | (hot << 16);
 }
 
+#ifndef DNG_NO_GENERAL_KERNELS	/* (fast_jit.cu only wants the shared parts) */
 /* ---- the kernel ------------------------------------------------------------ */
 
 __global__ void __launch_bounds__(DNG_NT, DNG_CTAS_PER_SM)
@@ -1126,7 +1128,6 @@ scan_kernel(const ScanArgs a)
 #define DNG_W_SLACK 64
 #define DNG_W_NLCAP 32				/* newline positions per pass */
 #define DNG_W_MAXLINE 512
-#define DNG_NW (DNG_NT / 32)
 
 static constexpr size_t SMEM_W_BUF = DNG_W_PRELAP + DNG_W_CHUNK + DNG_W_SLACK;
 /* per warp: window, newline positions, fallback queue, mbarrier */
@@ -1377,6 +1378,8 @@ scan_kernel_w(const ScanArgs a)
 
 	scan_epilogue(a, P, stab, C, s_mctr, nlong, ntmpl);
 }
+
+#endif /* DNG_NO_GENERAL_KERNELS */
 
 /* gather occupied entries: out[i] = {koff-1, klen, count} */
 struct OutEntry {

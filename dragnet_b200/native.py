@@ -77,6 +77,10 @@ _SIGS = [
     ('dng_scan_template_stats', ctypes.c_int,
      [_P, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     ('dng_scan_kernel_kind', ctypes.c_int, [_P]),
+    ('dng_scan_jit_stats', ctypes.c_int,
+     [_P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint64),
+      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+      ctypes.c_char_p, ctypes.c_size_t]),
     ('dng_scan_launch_count', ctypes.c_uint64, [_P]),
     ('dng_pinned_alloc', _P, [ctypes.c_size_t]),
     ('dng_pinned_free', None, [_P]),
@@ -349,10 +353,22 @@ class Scan(object):
         r = ctypes.c_uint64()
         _check(lib().dng_scan_template_stats(self.handle, ctypes.byref(t),
                                              ctypes.byref(r)), self.handle)
+        st = ctypes.c_int()
+        jl = ctypes.c_uint64()
+        cms = ctypes.c_double()
+        lms = ctypes.c_double()
+        err = ctypes.create_string_buffer(512)
+        _check(lib().dng_scan_jit_stats(self.handle, ctypes.byref(st),
+                                        ctypes.byref(jl), ctypes.byref(cms),
+                                        ctypes.byref(lms), err, len(err)),
+               self.handle)
+        kind = lib().dng_scan_kernel_kind(self.handle)
         return {'templates': int(t.value), 'templated_records': int(r.value),
-                'kernel': 'per-warp chunks'
-                if lib().dng_scan_kernel_kind(self.handle) == 1
-                else 'CTA tiles'}
+                'kernel': {0: 'CTA tiles', 1: 'per-warp chunks',
+                           2: 'F path'}.get(kind, str(kind)),
+                'jit': {'state': int(st.value), 'launches': int(jl.value),
+                        'compile_ms': cms.value, 'link_ms': lms.value,
+                        'error': err.value.decode('utf-8', 'replace')}}
 
     def close(self):
         if self.handle:

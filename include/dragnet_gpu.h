@@ -159,11 +159,21 @@ int dng_scan_template_stats(dng_scan *scan, uint64_t *templates,
     uint64_t *templated_records);
 
 /*
- * Which kernel geometry the scan runs (chosen from the sampled line lengths
- * at the first feed; environment DNG_KERNEL=tile|warp forces one): 0 = CTA-wide
- * tiles (any line length), 1 = per-warp chunks (short lines).
+ * Which kernel the scan runs (chosen from the plan and from a sample of the
+ * first data fed; environment DNG_KERNEL=tile|warp|fast forces one): 0 = CTA-wide
+ * tiles (any line length), 1 = per-warp chunks (short lines), 2 = the F path
+ * (templated input, plans it models: scan_kernel_f + the miss kernel).
  */
 int dng_scan_kernel_kind(const dng_scan *scan);
+/*
+ * The F path's run-time compiled matcher (NVRTC + nvJitLink, cached per
+ * process; environment DNG_JIT=0|async|sync, default async: scans use the
+ * interpreted matcher until the compiled one is there).  *state: 0 none / being
+ * built, 1 in use, 2 failed (message in err); *launches = scan launches that
+ * ran the compiled kernel; compile and link times in milliseconds.
+ */
+int dng_scan_jit_stats(dng_scan *scan, int *state, uint64_t *launches,
+    double *compile_ms, double *link_ms, char *err, size_t errlen);
 /* Every kernel this scan has launched so far: scan kernels plus the small
  * ones around them (template resolution, newline search of device feeds,
  * result compaction). */

@@ -41,11 +41,20 @@ def build_hostcheck():
             os.path.join(CSRC, 'tmpl.cpp'), os.path.join(CSRC, 'fast.cpp')]
     deps = srcs + [os.path.join(CSRC, n) for n in
                    ('record.cuh', 'jsnum.cuh', 'jsdate.cuh', 'plan.h',
-                    'result.h', 'tmpl.h', 'tmpl.cuh', 'fast.h', 'fast.cuh')]
+                    'result.h', 'tmpl.h', 'tmpl.cuh', 'fast.h', 'fast.cuh',
+                    'fscan.cuh')]
+    srcs.append(os.path.join(CSRC, 'jit.cpp'))
+    deps += [os.path.join(CSRC, 'jit.cpp'), os.path.join(CSRC, 'jit.h'),
+             os.path.join(CSRC, 'fast_kernel.cuh'),
+             os.path.join(CSRC, 'fast_jit.cu')]
     if not os.path.exists(exe) or \
             os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(['g++', '-std=c++17', '-O1', '-g', '-o', exe] +
-                              srcs)
+        # the relocatable kernel + fscan.cuh as data (jit.cpp links them in)
+        subprocess.check_call(['make', '-s', '-C', CSRC, 'build/jit_blob.o'])
+        subprocess.check_call(['g++', '-std=c++17', '-O1', '-g',
+                               '-I/usr/local/cuda/include', '-o', exe] +
+                              srcs + [os.path.join(CSRC, 'build',
+                                                   'jit_blob.o'), '-ldl'])
     return exe
 
 

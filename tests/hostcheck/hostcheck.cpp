@@ -20,6 +20,9 @@
 #include "../../dragnet_b200/csrc/record.cuh"
 #include "../../dragnet_b200/csrc/tmpl.cuh"
 #include "../../dragnet_b200/csrc/fast.cuh"
+#include "../../dragnet_b200/csrc/jit.h"
+#include <dlfcn.h>
+#include <unistd.h>
 #include "../../dragnet_b200/csrc/result.h"
 #include "../../include/dragnet_gpu.h"
 
@@ -31,6 +34,93 @@ static std::string slurp(const char *path)
 	std::stringstream ss;
 	ss << f.rdbuf();
 	return ss.str();
+}
+
+/*
+ * DNG_HOSTCHECK_JIT: the matcher the run-time compiler generates for the F
+ * templates (jit.cpp), two ways: (1) the real thing -- NVRTC + nvJitLink against
+ * the relocatable kernel embedded in the library -- must build (no GPU needed
+ * for that); (2) the same generated code compiled for the HOST with a prelude
+ * that maps its shared-memory accessors onto a byte array, and used below in
+ * place of fmatch(), so that its control flow and immediates are checked
+ * against the oracle like everything else.
+ */
+static const char *HOST_PRELUDE =
+"#include <stdint.h>\n#include <string.h>\n"
+"typedef uint8_t u8; typedef uint32_t u32; typedef uint64_t u64;\n"
+"#define DNG_HD static inline\n#define __device__\n"
+"enum { T_UNDEF = 0, T_NULL = 1, T_FALSE = 2, T_TRUE = 3, T_NUM = 4, T_STR = 5 };\n"
+"#define DNG_FCAP(type, off, len, flag) \\\n"
+"	((u32)(off) | ((u32)(len) << 12) | ((u32)(type) << 24) | ((u32)(flag) << 27))\n"
+"DNG_HD bool is_hex(u32 c) { return (c >= '0' && c <= '9') || ((c | 0x20) >= 'a' && (c | 0x20) <= 'f'); }\n"
+"DNG_HD u32 tm_isdigit(u32 c) { return c - '0' <= 9u; }\n"
+"DNG_HD u32 nondigit_mask(u32 w) { const u32 x = w ^ 0x30303030u; return (((x & 0x7f7f7f7fu) + 0x76767676u) | x) & 0x80808080u; }\n"
+"DNG_HD u32 low_flag_byte(u32 m) { u32 k = 0; while (!((m >> (8 * k + 7)) & 1)) k++; return k; }\n"
+"extern \"C\" unsigned char *dng_jit_host_mem;\nunsigned char *dng_jit_host_mem;\n"
+"DNG_HD u32 jlds32(u32 a) { u32 v; memcpy(&v, dng_jit_host_mem + a, 4); return v; }\n"
+"DNG_HD u32 jlds8(u32 a) { return dng_jit_host_mem[a]; }\n"
+"DNG_HD void jsts32(u32 a, u32 v) { memcpy(dng_jit_host_mem + a, &v, 4); }\n"
+"DNG_HD u32 __funnelshift_r(u32 lo, u32 hi, u32 sh) { return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }\n"
+"struct JMem {\n	u32 ra;\n	struct Cur { u32 wa, w0, w1, sh;\n"
+"		u32 next() { const u32 d = __funnelshift_r(w0, w1, sh); w0 = w1; wa += 4; w1 = jlds32(wa); return d; } };\n"
+"	Cur cursor(u32 off) const { Cur c; const u32 a = ra + off; c.sh = (a & 3) * 8; c.wa = (a & ~3u) + 4;\n"
+"		c.w0 = jlds32(c.wa - 4); c.w1 = jlds32(c.wa); return c; }\n"
+"	u32 byte(u32 off) const { return jlds8(ra + off); }\n"
+"	u32 word(u32 off) const { Cur c = cursor(off); return c.next(); }\n};\n";
+
+typedef unsigned (*jmatch_fn)(unsigned, unsigned, unsigned, unsigned);
+
+static jmatch_fn host_jit(const std::vector<u8> &fblob, unsigned char ***mem)
+{
+	std::string dev = jit_source(fblob.data(), fblob.size());
+	std::string cubin, err;
+	double cms = 0, lms = 0;
+	/* DNG_HOSTCHECK_JIT=2: the device build too (a second or two) */
+	if (atoi(getenv("DNG_HOSTCHECK_JIT")) >= 2) {
+		if (!jit_build(dev, cubin, err, &cms, &lms)) {
+			fprintf(stderr, "jit_build: %s\n", err.c_str());
+			exit(4);
+		}
+		fprintf(stderr, "jit: %zu bytes of source, nvrtc %.0f ms, link "
+		    "%.0f ms, cubin %zu bytes\n", dev.size(), cms, lms,
+		    cubin.size());
+	}
+	if (const char *dump = getenv("DNG_HOSTCHECK_JIT_DUMP")) {
+		FILE *d1 = fopen((std::string(dump) + ".cu").c_str(), "w");
+		fwrite(dev.data(), 1, dev.size(), d1);
+		fclose(d1);
+		FILE *d2 = fopen((std::string(dump) + ".cubin").c_str(), "w");
+		fwrite(cubin.data(), 1, cubin.size(), d2);
+		fclose(d2);
+	}
+	std::string host = jit_source(fblob.data(), fblob.size(), HOST_PRELUDE);
+	char dir[] = "/tmp/dng_jit_XXXXXX";
+	if (!mkdtemp(dir))
+		exit(4);
+	std::string src = std::string(dir) + "/jm.cpp", so = std::string(dir) +
+	    "/jm.so";
+	FILE *f = fopen(src.c_str(), "w");
+	fwrite(host.data(), 1, host.size(), f);
+	fclose(f);
+	std::string cmd = "g++ -std=c++17 -O1 -w -shared -fPIC -o " + so + " " + src;
+	if (system(cmd.c_str()) != 0) {
+		fprintf(stderr, "host build of the generated matcher failed: %s\n",
+		    src.c_str());
+		exit(4);
+	}
+	void *h = dlopen(so.c_str(), RTLD_NOW);
+	if (!h) {
+		fprintf(stderr, "dlopen: %s\n", dlerror());
+		exit(4);
+	}
+	*mem = (unsigned char **)dlsym(h, "dng_jit_host_mem");
+	jmatch_fn fn = (jmatch_fn)dlsym(h, "dng_jmatch");
+	unlink(src.c_str());
+	unlink(so.c_str());
+	rmdir(dir);
+	if (!fn || !*mem)
+		exit(4);
+	return fn;
 }
 
 int main(int argc, char **argv)
@@ -108,6 +198,13 @@ int main(int argc, char **argv)
 			tmpl_build(cands, res, 60000, fblob, nullptr, true);
 		}
 	}
+	jmatch_fn jm = nullptr;
+	unsigned char **jmem = nullptr;
+	static unsigned char jbuf[65536];
+	if (getenv("DNG_HOSTCHECK_JIT") != nullptr && !fblob.empty()) {
+		jm = host_jit(fblob, &jmem);
+		*jmem = jbuf;
+	}
 	static LocalCounters MCs[MAX_METRICS];
 	memset(MCs, 0, sizeof (MCs));
 	std::map<std::string, uint64_t> table;
@@ -129,7 +226,22 @@ int main(int argc, char **argv)
 			u32 defmask = 0;
 			double s0 = 0, s1 = 0;
 			u32 fo = FO_MISS, h = 0, klen = 0, slow = 0;
-			if (fmatch(fm, len, true, defmask))
+			bool matched;
+			if (jm) {
+				/* the record at an odd address of the fake shared
+				 * memory, '\n' after it, captures in rows of 768 */
+				const u32 ra = 1027, caps = 32768;
+				memcpy(jbuf + ra, rec, len);
+				memset(jbuf + ra + len, '\n', 64);
+				const unsigned r = jm(ra, len, 1, caps);
+				matched = r & 1;
+				defmask = r >> 1;
+				for (u32 k = 0; k < F_MAXPATHS; k++)
+					memcpy(&fm.caps[k], jbuf + caps + k * 768 * 4, 4);
+			} else {
+				matched = fmatch(fm, len, true, defmask);
+			}
+			if (matched)
 				fo = fstage(fm, FP, defmask, s0, s1);
 			if (fo == FO_AGGR &&
 			    (!fprep(fm, FP, defmask, s0, s1, slow) ||

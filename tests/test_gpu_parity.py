@@ -16,14 +16,34 @@ from golden_harness import check_section  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['auto', 'tile', 'warp', 'fast'], autouse=True)
+# under 'jit' every distinct template set costs a second or two of compilation:
+# the cases that exercise the matcher, not all of them
+JIT_TESTS = {'test_reference_goldens_through_c_abi', 'test_edge_lines',
+             'test_synthetic_matches_oracle',
+             'test_scalar_forms_behind_one_template',
+             'test_optional_fields_make_a_branching_trie',
+             'test_template_fuzz', 'test_chunk_boundaries_do_not_matter'}
+
+
+@pytest.fixture(params=['auto', 'tile', 'warp', 'fast', 'jit'], autouse=True)
 def kernel_geometry(request, monkeypatch):
     """Every case under the general kernels' two geometries (CTA-wide tiles,
     per-warp chunks), under the F path forced on (scan_kernel_f + the miss
     kernel, whatever the templates cover) and under the library's own choice
     between them."""
     monkeypatch.delenv('DNG_KERNEL', raising=False)
-    if request.param != 'auto':
+    monkeypatch.delenv('DNG_JIT', raising=False)
+    if request.param == 'jit':
+        # the F path with the matcher compiled at run time for the templates
+        # (jit.cpp), waited for; 'fast' = the same with the interpreted one
+        if request.node.originalname not in JIT_TESTS:
+            pytest.skip('not a matcher test')
+        monkeypatch.setenv('DNG_KERNEL', 'fast')
+        monkeypatch.setenv('DNG_JIT', 'sync')
+    elif request.param == 'fast':
+        monkeypatch.setenv('DNG_KERNEL', 'fast')
+        monkeypatch.setenv('DNG_JIT', '0')
+    elif request.param != 'auto':
         monkeypatch.setenv('DNG_KERNEL', request.param)
 
 
@@ -273,11 +293,18 @@ def test_templates_with_unmatched_records_in_the_same_tile(tmp_path):
         assert act_c == exp_c, argv
 
 
-def test_scalar_forms_behind_one_template(tmp_path):
+@pytest.mark.parametrize('pad', [b'', b'"host":"padding-padding-padding-x",'])
+def test_scalar_forms_behind_one_template(pad, tmp_path):
     """Every number / literal / string-body form in one record shape, so that
-    the template's wildcard scans see them all (see tests/corpus.py)."""
+    the template's wildcard scans see them all (see tests/corpus.py).  The
+    padded variant makes the lines long enough for the F kernel's chunks
+    (more than 128 lines per chunk go to the general parser as they are)."""
     from dragnet_b200 import datasource_gpu
     lines = [b'{"a":7,"s":"k0"}'] * 3 + corpus.scalar_lines()
+    lines = [b'{' + pad + ln[1:] for ln in lines]
+    if os.environ.get('DNG_KERNEL') == 'fast' and not pad:
+        pytest.skip('lines of 16 bytes: the F kernel hands them all over')
+    jit_expected = os.environ.get('DNG_JIT') == 'sync'
     path = _write(tmp_path, 'scalars.log', lines)
     for argv in (['-b', 'a'], ['-b', 's'], ['-b', 'a[aggr=quantize]'],
                  ['-b', 'a,s', '-f', '{"ge":["a",1]}']):
@@ -287,6 +314,9 @@ def test_scalar_forms_behind_one_template(tmp_path):
         assert canon_points(r.points) == canon_points(exp_p), argv
         assert r.counters == exp_c, argv
         assert r.stats['templated_records'] > 20, r.stats
+        if jit_expected:
+            assert r.stats['jit']['state'] == 1, r.stats
+            assert r.stats['jit']['launches'] >= 1, r.stats
 
 
 @pytest.mark.parametrize('pad', [0, 40, 90, 140, 260, 380, 700])

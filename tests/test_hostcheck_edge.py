@@ -8,7 +8,7 @@ import sys
 import pytest
 
 
-@pytest.fixture(params=['general', 'fast', 'tmpl', 'fpath'], autouse=True)
+@pytest.fixture(params=['general', 'fast', 'tmpl', 'fpath', 'jit'], autouse=True)
 def parser_mode(request, monkeypatch):
     """Run every case with the general parser only, with the lock-step fast
     automaton (+ fallback), and with record templates learned from the input
@@ -18,8 +18,13 @@ def parser_mode(request, monkeypatch):
     monkeypatch.delenv('DNG_HOSTCHECK_FAST', raising=False)
     monkeypatch.delenv('DNG_HOSTCHECK_TMPL', raising=False)
     monkeypatch.delenv('DNG_HOSTCHECK_F', raising=False)
-    if request.param == 'fpath':
+    monkeypatch.delenv('DNG_HOSTCHECK_JIT', raising=False)
+    if request.param in ('fpath', 'jit'):
         monkeypatch.setenv('DNG_HOSTCHECK_F', '1')
+    if request.param == 'jit':
+        # + the matcher jit.cpp generates for the templates: built for the
+        # device (NVRTC + nvJitLink, no GPU needed) and run on the host
+        monkeypatch.setenv('DNG_HOSTCHECK_JIT', '1')
     if request.param in ('fast', 'tmpl'):
         monkeypatch.setenv('DNG_HOSTCHECK_FAST', '1')
     if request.param == 'tmpl':

@@ -34,7 +34,9 @@ for cub in glob.glob(os.path.join(d, 'api*.cubin')):
         if m:
             fl, ln = m.group(1).split('/')[-1], int(m.group(2))
         m = re.match(r'^\s*/\*([0-9a-f]{4,})\*/\s+(\S.*?);', l)
-        if m and fn and (os.environ.get('NCU_FN', 'scan_kernel_w') + 'ENS_8ScanArgs') in fn:
+        want = os.environ.get('NCU_FN', 'scan_kernel_w')
+        if m and fn and ((want + 'ENS_8ScanArgs') in fn or
+                         ('fILi' in want and want in fn)):
             addr2line[int(m.group(1), 16)] = (fl, ln)
 skip = os.environ.get('NCU_SKIP', '0')
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv',
