@@ -367,7 +367,19 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 				s->wslice = sl;
 			}
 		}
-		s->f_nsl = s->wslice / 16;
+		/* the F kernel indexes at most DNG_F_NLCAP lines per chunk:
+		 * the largest such slice with the best lane use */
+		best = -1;
+		s->f_nsl = 7;
+		for (u32 sl = 112; sl <= DNG_W_SLICE_MAX; sl += 32) {
+			double recs = 32.0 * sl / mean;
+			double passes = ceil((recs + 1.5) / 32.0);
+			double util = recs / (32.0 * passes);
+			if (recs * 1.25 <= DNG_F_NLCAP && util >= best) {
+				best = util;
+				s->f_nsl = sl / 16;
+			}
+		}
 	}
 	if (!s->tmpl_enabled)
 		return 0;

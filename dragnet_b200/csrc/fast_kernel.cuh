@@ -429,19 +429,18 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 			 * the positions.
 			 */
 			const u32 c0 = D0 + lane * SLICE;
-			u32 hot = 0, cnt = 0;
+			u32 hot = 0, cnt = 0, one = 0;
 #pragma unroll
 			for (u32 j = 0; j < (u32)NSL; j++) {
+				/* any byte <= '\n' in these 16?  (b - 0x0b borrows
+				 * exactly for those; a borrow into the next byte can
+				 * only add a flag) */
 				const uint4 v = lds128(sb + c0 + 16 * j);
-				const u32 x0 = v.x ^ 0x0a0a0a0au;
-				const u32 x1 = v.y ^ 0x0a0a0a0au;
-				const u32 x2 = v.z ^ 0x0a0a0a0au;
-				const u32 x3 = v.w ^ 0x0a0a0a0au;
-				const u32 t = (((x0 - 0x01010101u) & ~x0) |
-				    ((x1 - 0x01010101u) & ~x1) |
-				    ((x2 - 0x01010101u) & ~x2) |
-				    ((x3 - 0x01010101u) & ~x3)) & 0x80808080u;
-				if (t)
+				u32 t = (v.x - 0x0b0b0b0bu) & ~v.x;
+				t |= (v.y - 0x0b0b0b0bu) & ~v.y;
+				t |= (v.z - 0x0b0b0b0bu) & ~v.z;
+				t |= (v.w - 0x0b0b0b0bu) & ~v.w;
+				if (t & 0x80808080u)
 					hot |= 1u << j;
 			}
 #pragma unroll 1
@@ -449,8 +448,16 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 				const u32 p = c0 + 16 * (__ffs(hm) - 1);
 				const uint4 v = lds128(sb + p);
 				if (p >= lo && p + 16 <= hi) {
-					cnt += __popc(nl_mask(v.x)) + __popc(nl_mask(v.y)) +
-					    __popc(nl_mask(v.z)) + __popc(nl_mask(v.w));
+					const u32 m0 = nl_mask(v.x), m1 = nl_mask(v.y);
+					const u32 m2 = nl_mask(v.z), m3 = nl_mask(v.w);
+					const u32 k = __popc(m0) + __popc(m1) +
+					    __popc(m2) + __popc(m3);
+					/* (the usual case, one newline per lane: its
+					 * position right away) */
+					if (k == 1)
+						one = p + (m0 ? 0 : m1 ? 4 : m2 ? 8 : 12) +
+						    ((__ffs(m0 | m1 | m2 | m3) - 1) >> 3);
+					cnt += k;
 				} else {
 					/* the ends of the input: byte by byte */
 					for (u32 x = 0; x < 16; x++)
@@ -504,7 +511,9 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 				if (last >= 0)
 					beg0 = last + 1;
 			} else if (total) {
-				{
+				if (cnt == 1 && one) {
+					nlpos[mybase] = (unsigned short)one;
+				} else if (cnt) {
 					u32 idx = mybase;
 #pragma unroll 1
 					for (u32 hm = hot; hm; hm &= hm - 1) {
