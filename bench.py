@@ -4,17 +4,28 @@
   python bench.py --gpus N --steps K --warmup W            (our CUDA path)
   python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
 
-Workload (BASELINE.json configs[1]): 100 M rows of mktestdata-shaped NDJSON per
-GPU (~22.4 GB, generated on the device, deterministic), `dn scan -b req.method`.
-A step is one full scan of the shard (+ the NCCL merge of the tallies when
-N > 1).  `value` = records of all ranks / device time with the input resident in
-HBM; `e2e` = the same scan fed from pinned HOST buffers through the public C
-ABI (dng_scan_feed_pinned: H2D inside the timed region); `roofline` = algorithmic
-input bytes / scan-kernel time (CUDA events on the launch stream) against the
-measured HBM copy peak; `cpu_baseline` = oracle/dn_oracle.cpp (restated CPU
-reference: node + the reference's npm dependencies do not exist in this image)
-on a bounded sample, all host threads.  Inputs (22 GB) are far larger than L2
-(126 MB), so no explicit L2 flush is needed between iterations.
+Workload (BASELINE.json configs[2], the north star's own target shape): 100 M
+rows of mktestdata-shaped NDJSON per GPU (~22.4 GB, generated on the device,
+deterministic), `dn scan -b req.method,res.statusCode -f {"eq":["req.method",
+"GET"]}`.  A step is one full scan of the shard (+ the NCCL merge of the tallies
+when N > 1).  `value` = records of all ranks / device time with the input
+resident in HBM; `e2e` = the same scan fed from pinned HOST buffers through the
+public C ABI (dng_scan_feed_pinned: H2D inside the timed region), its tallies
+checked against the oracle's, with the PCIe roofline from a pinned-copy probe of
+the same run; `roofline` = algorithmic input bytes / scan-kernel time (CUDA
+events on the launch stream) against the measured HBM copy peak; `configs` =
+the other BASELINE configs (C2, C4, C5 resident; configs[3]'s 1 B rows streamed
+from a cycled pinned pool with the expected counts); `cpu_baseline` =
+oracle/dn_oracle.cpp (restated CPU reference: node + the reference's npm
+dependencies do not exist in this image) on a bounded sample, 1 thread and all
+host threads.  Inputs (22 GB) are far larger than L2 (126 MB), so no explicit
+L2 flush is needed between iterations.
+
+The scan compiles its matcher at run time (NVRTC + nvJitLink, cached per
+process: dragnet_b200/csrc/jit.h); bench.py asks for the synchronous mode
+(DNG_JIT=sync), so the compilation (about a second, once per query shape)
+happens in the warm-up steps and every timed step includes the template
+learning and the cache lookup a scan does.
 """
 
 import argparse
@@ -38,7 +49,7 @@ QUERIES = {
             '{"eq":["req.method","GET"]}'], None,
            'configs[2]: 100M rows, -b req.method,res.statusCode + krill eq'),
     'C4': (['-b', 'latency[aggr=quantize]'], None,
-           'configs[3]: -b latency[aggr=quantize]'),
+           'configs[3]: -b latency[aggr=quantize] numeric histogram'),
     'C5': (['-b', 'operation,req.method,host'], None,
            'configs[4]: 3-key breakdown, NCCL final reduce'),
 }
@@ -146,44 +157,44 @@ def canon(points):
 
 
 # ---------------------------------------------------------------------------
-# CPU reference arm / cpu_baseline
+# CPU reference arm / cpu_baseline: oracle/ only (no product library)
 # ---------------------------------------------------------------------------
 
-def oracle_exe():
+def oracle_build():
     exe = os.path.join(ROOT, 'oracle', 'dn_oracle_cpp')
-    if not os.path.exists(exe):
+    gen = os.path.join(ROOT, 'oracle', 'gen_ndjson')
+    if not (os.path.exists(exe) and os.path.exists(gen)):
         subprocess.check_call(['make', '-s', '-C',
                                os.path.join(ROOT, 'oracle')])
-    return exe
+    return exe, gen
 
 
-def run_oracle(plan, path, threads, repeat=1):
+def run_oracle(plan, path, threads, repeat=1, min_seconds=0.0):
+    exe, _ = oracle_build()
     with tempfile.NamedTemporaryFile('w', suffix='.json', delete=False) as f:
         json.dump(plan, f)
         pf = f.name
     try:
-        out = subprocess.run([oracle_exe(), pf, '--threads', str(threads),
-                              '--repeat', str(repeat), path],
-                             capture_output=True, check=True).stdout
+        out = subprocess.run([exe, pf, '--threads', str(threads), '--repeat',
+                              str(repeat), '--min-seconds', str(min_seconds),
+                              path], capture_output=True, check=True).stdout
     finally:
         os.unlink(pf)
     return json.loads(out)
 
 
-def sample_file(rows, seed, total_rows):
-    """The first `rows` records of the `total_rows`-record workload, written
-    to tmpfs (host generator: byte-identical to the device generator)."""
-    from dragnet_b200 import native
+def sample_file(rows, seed, total_rows, first=0):
+    """Records [first, first + rows) of the `total_rows`-record workload of
+    `seed`, written to tmpfs by oracle/gen_ndjson (byte-identical to the device
+    generator: tests/test_gpu_parity.py, tests/test_cabi_cpu.py)."""
+    _, gen = oracle_build()
     d = '/dev/shm' if os.path.isdir('/dev/shm') else tempfile.gettempdir()
-    path = os.path.join(d, 'dnbench_sample_%d_%d_%d.ndjson' %
-                        (seed, rows, total_rows))
+    path = os.path.join(d, 'dnbench_sample_%d_%d_%d_%d.ndjson' %
+                        (seed, first, rows, total_rows))
     if not os.path.exists(path):
-        params = native.gen_params(seed=seed, total_records=total_rows)
-        with open(path + '.tmp', 'wb') as f:
-            step = 250000
-            for first in range(0, rows, step):
-                f.write(native.gen_host(params, first,
-                                        min(step, rows - first)))
+        subprocess.check_call([gen, path + '.tmp', str(seed), str(total_rows),
+                               str(first), str(rows),
+                               str(min(32, os.cpu_count() or 1))])
         os.rename(path + '.tmp', path)
     return path
 
@@ -203,9 +214,32 @@ def oracle_points(doc):
     return pts
 
 
+def cpu_baseline(plan, rows, total_rows, seed, threads, min_seconds):
+    """The restated CPU reference on a bounded sample: all threads and one."""
+    path = sample_file(rows, seed, total_rows)
+    many = run_oracle(plan, path, threads, min_seconds=min_seconds)
+    # one thread: a quarter of the sample is plenty (about 0.4 M records/s)
+    rows1 = max(1, rows // 8)
+    path1 = sample_file(rows1, seed, total_rows)
+    one = run_oracle(plan, path1, 1, min_seconds=min(min_seconds, 1.0))
+    return {
+        'value': rows / many['mean_seconds'], 'unit': 'records/s',
+        'cores': threads, 'kind': 'port',
+        'best_value': rows / many['seconds'],
+        'one_thread_value': rows1 / one['mean_seconds'],
+        'sample': 'first %d rows (%.2f GB) of the workload, %d threads, '
+                  'file-range sharded, mean of %d scans (>= %.1f s measured); '
+                  'one thread: first %d rows; restated CPU oracle '
+                  '(oracle/dn_oracle.cpp, -O3): the reference Node path is '
+                  'not executable here (no node in the image)' %
+                  (rows, os.path.getsize(path) / 1e9, threads, many['reps'],
+                   min_seconds, rows1)}, many
+
+
 def reference_arm(args, rank, world):
     """--impl reference: the restated CPU reference (oracle/dn_oracle.cpp) on
-    all host threads; a step = one scan of a bounded sample of the workload."""
+    all host threads; a step = scans of a bounded sample of the workload for
+    at least two seconds.  Nothing of the product library is loaded."""
     if rank != 0:
         return
     argv, ds, desc = QUERIES[args.query]
@@ -215,30 +249,39 @@ def reference_arm(args, rank, world):
     path = sample_file(rows, 0xD5A60000, args.rows)
     for _ in range(max(args.warmup, 1)):
         run_oracle(plan, path, threads)
-    secs = []
+    per, reps = [], 0
     for _ in range(args.steps):
-        secs.append(run_oracle(plan, path, threads)['seconds'])
-    per = sum(secs) / len(secs)
-    value = rows / per
+        d = run_oracle(plan, path, threads, min_seconds=2.0)
+        per.append(d['mean_seconds'])
+        reps += d['reps']
+    mean = sum(per) / len(per)
+    value = rows / mean
+    rows1 = max(1, rows // 8)
+    one = run_oracle(plan, sample_file(rows1, 0xD5A60000, args.rows), 1,
+                     min_seconds=1.0)
     line = {
         'impl': 'reference', 'metric': 'json_records_per_sec',
         'value': value, 'unit': 'records/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': per * 1e3, 'higher_is_better': True,
+        'ms_per_step': mean * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
         'data': 'synthetic',
-        'config': {'workload': desc, 'rows_per_step': rows,
+        'config': {'workload': desc, 'rows_per_scan': rows,
+                   'scans_per_step': reps / float(args.steps),
                    'query': ' '.join(argv),
                    'note': 'CPU reference arm: C++ restatement of the '
                            'reference Node.js scan path (node and the '
                            "reference's npm dependencies are not in this "
-                           'image); bounded sample of the 100M-row workload'},
+                           'image); bounded sample of the 100M-row workload, '
+                           'scanned repeatedly for >= 2 s per step'},
         'cpu_baseline': {'value': value, 'unit': 'records/s',
                          'cores': threads, 'kind': 'port',
+                         'one_thread_value': rows1 / one['mean_seconds'],
                          'sample': '%d rows (%.2f GB) of the workload, %d '
-                                   'threads, file-range sharded' %
+                                   'threads, file-range sharded, mean over '
+                                   '%d scans' %
                                    (rows, os.path.getsize(path) / 1e9,
-                                    threads)},
+                                    threads, reps)},
         'e2e': {'value': value, 'unit': 'records/s',
                 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -250,9 +293,37 @@ def reference_arm(args, rank, world):
 # GPU arm
 # ---------------------------------------------------------------------------
 
+def pcie_probe(torch, dev, nbytes=1 << 30, reps=4):
+    """Pinned host -> device cudaMemcpyAsync bandwidth (GB/s), best of reps."""
+    src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(nbytes, dtype=torch.uint8, device='cuda:%d' % dev)
+    best = 0.0
+    for _ in range(reps + 1):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dst.copy_(src, non_blocking=True)
+        e1.record()
+        e1.synchronize()
+        best = max(best, nbytes / 1e9 / (e0.elapsed_time(e1) / 1e3))
+    del src, dst
+    return best
+
+
+def kernel_name(st):
+    if st['kernel'] == 'F path':
+        if st['jit']['launches']:
+            return ('dng_scan_kernel_j (scan_kernel_f with the run-time '
+                    'compiled matcher)')
+        return 'dng::scan_kernel_f'
+    return 'dng::scan_kernel_w' if st['kernel'] == 'per-warp chunks' \
+        else 'dng::scan_kernel'
+
+
 def gpu_arm(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
+    os.environ.setdefault('DNG_JIT', 'sync')
     from dragnet_b200 import native
 
     torch.cuda.set_device(local_rank)
@@ -262,7 +333,6 @@ def gpu_arm(args, rank, local_rank, world):
     L = native.lib()
     argv, ds, desc = QUERIES[args.query]
     plan = make_plan(argv, ds)
-    plan_json = json.dumps(plan, separators=(',', ':'))
     rows = args.rows
     seed = 0xD5A60000 + rank
     # clocks / throttle reasons of every GPU of the job, sampled by rank 0 from
@@ -310,11 +380,18 @@ def gpu_arm(args, rank, local_rank, world):
             raise RuntimeError('dng_comm_init: %s' % err.value)
 
     stream = torch.cuda.current_stream().cuda_stream
-    p_handle = native.Plan(plan_json)
+    handles = {}
 
-    def one_scan(feed, merge=True):
+    def plan_handle(q):
+        if q not in handles:
+            a, d, _ = QUERIES[q]
+            handles[q] = native.Plan(json.dumps(make_plan(a, d),
+                                                separators=(',', ':')))
+        return handles[q]
+
+    def one_scan(feed, merge=True, q=None):
         """-> (points or None, counters, kernel stats, device ms)"""
-        s = native.Scan(p_handle, dev)
+        s = native.Scan(plan_handle(q or args.query), dev)
         s.set_stream(stream)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -348,7 +425,7 @@ def gpu_arm(args, rank, local_rank, world):
     def feed_resident(s):
         s.feed_device(buf.data_ptr(), nbytes)
 
-    # ---- pinned host pool for the end-to-end leg ------------------------------
+    # ---- pinned host pool for the end-to-end legs -----------------------------
     # the first pool_rows records of the shard, copied out of HBM once; their
     # byte length is what the generator reports for that record range
     tmp = torch.empty(pool_rows * 226 + (1 << 20), dtype=torch.uint8,
@@ -364,19 +441,21 @@ def gpu_arm(args, rank, local_rank, world):
     cycles = max(1, rows // pool_rows)
     e2e_rows = cycles * pool_rows
 
-    def feed_host(s):
-        for _ in range(cycles):
-            s.feed_pinned(host_pool.data_ptr(), pool_len)
+    def feed_host_n(n):
+        def feed(s):
+            for _ in range(n):
+                s.feed_pinned(host_pool.data_ptr(), pool_len)
+        return feed
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(feed, steps, warmup):
+    def timed(feed, steps, warmup, q=None):
         res = None
         for _ in range(warmup):
-            res = one_scan(feed)
+            res = one_scan(feed, q=q)
         barrier()
         if sampler is not None:
             sampler.mark()
@@ -385,7 +464,7 @@ def gpu_arm(args, rank, local_rank, world):
         tail_ms = 0.0
         all_launches = 0
         for _ in range(steps):
-            res = one_scan(feed)
+            res = one_scan(feed, q=q)
             dev_ms += res[3]
             tail_ms += res[2]['after_feed_ms']
             kern_ms += res[2]['kernel_ms']
@@ -405,6 +484,9 @@ def gpu_arm(args, rank, local_rank, world):
                 'launches': launches, 'all_launches': all_launches,
                 'clocks': clocks, 'last': res}
 
+    peak, how = measured_peaks()
+    cpu_threads = max(1, (os.cpu_count() or 1) // world)
+
     # ---- value: input resident in HBM -------------------------------------------
     R = timed(feed_resident, args.steps, args.warmup)
     ms_per_step = R['dev_ms'] / args.steps
@@ -412,7 +494,7 @@ def gpu_arm(args, rank, local_rank, world):
     value = total_rows / (ms_per_step / 1e3)
 
     # ---- e2e: host buffers through the public C ABI ------------------------------
-    E = timed(feed_host, max(1, args.e2e_steps), 1)
+    E = timed(feed_host_n(cycles), max(1, args.e2e_steps), 1)
     e2e_ms = E['dev_ms'] / max(1, args.e2e_steps)
     e2e_value = e2e_rows * world / (e2e_ms / 1e3)
     result_bytes = 0
@@ -420,41 +502,126 @@ def gpu_arm(args, rank, local_rank, world):
         result_bytes = sum(8 + sum(len(c) if isinstance(c, bytes) else 8
                                    for c in cols)
                            for cols, _ in E['last'][0])
+    h2d_peak = pcie_probe(torch, dev)
+
+    # ---- what the oracle says about this rank's pool and about a sample ------
+    # (every rank checks its own shard; the oracle's threads are shared out)
+    def oracle_tallies(q, path):
+        a, d, _ = QUERIES[q]
+        doc = run_oracle(make_plan(a, d), path, cpu_threads)
+        return {tuple(repr(c) for c in cols): v
+                for cols, v in oracle_points(doc)}, doc
+
+    pool_path = sample_file(pool_rows, seed, rows)
+    assert os.path.getsize(pool_path) == pool_len
+    pool_exp, pool_doc = oracle_tallies(args.query, pool_path)
+
+    def times(tallies, k):
+        return {key: v * k for key, v in tallies.items()}
+
+    def as_dict(points):
+        return {tuple(repr(c) for c in cols): v for cols, v in points}
+
+    # the e2e leg's own result: at N > 1 the merged tallies are checked below
+    e2e_local = one_scan(feed_host_n(cycles), merge=False)
+    e2e_parity = 'exact' if as_dict(e2e_local[0]) == times(pool_exp, cycles) \
+        and e2e_local[1]['lines'] == pool_doc['counters']['lines'] * cycles \
+        else 'MISMATCH'
 
     # ---- files: the same pool as a tmpfs file through dng_scan_feed_file -------
     file_leg = None
     if world == 1 and args.file_steps > 0:
-        d = '/dev/shm' if os.path.isdir('/dev/shm') else tempfile.gettempdir()
-        fpath = os.path.join(d, 'dnbench_pool_%d.ndjson' % os.getpid())
-        host_pool.numpy().tofile(fpath)
-        try:
-            Fr = timed(lambda s: s.feed_file(fpath), args.file_steps, 1)
-            fms = Fr['dev_ms'] / args.file_steps
-            file_leg = {'value': pool_rows / (fms / 1e3),
-                        'unit': 'records/s', 'ms_per_step': fms,
-                        'file_bytes': pool_len,
-                        'gbs': pool_len / 1e9 / (fms / 1e3),
-                        'note': 'dng_scan_feed_file on a page-cache-resident '
-                                'file: reader threads pread into a pinned '
-                                'ring, H2D overlapped with the scan'}
-        finally:
-            os.unlink(fpath)
+        Fr = timed(lambda s: s.feed_file(pool_path), args.file_steps, 1)
+        fms = Fr['dev_ms'] / args.file_steps
+        file_leg = {'value': pool_rows / (fms / 1e3),
+                    'unit': 'records/s', 'ms_per_step': fms,
+                    'file_bytes': pool_len,
+                    'gbs': pool_len / 1e9 / (fms / 1e3),
+                    'parity': 'exact' if as_dict(Fr['last'][0]) == pool_exp
+                    else 'MISMATCH',
+                    'note': 'dng_scan_feed_file on a page-cache-resident '
+                            'file: reader threads pread into a pinned '
+                            'ring, H2D overlapped with the scan'}
 
-    # ---- N > 1: the merged tallies must equal the sum of the per-rank ones ----
+    # ---- the other BASELINE configs, resident in HBM ---------------------------
+    configs = []
+    for q in ('C2', 'C3', 'C4', 'C5'):
+        C = R if q == args.query else timed(feed_resident, args.cfg_steps, 1,
+                                            q=q)
+        steps = args.steps if q == args.query else args.cfg_steps
+        cms = C['dev_ms'] / steps
+        gbs = (C['kernel_bytes'] / 1e9) / (C['kernel_ms'] / 1e3)
+        configs.append({
+            'config': QUERIES[q][2], 'query': ' '.join(QUERIES[q][0]),
+            'rows_per_gpu': rows, 'value': total_rows / (cms / 1e3),
+            'unit': 'records/s', 'ms_per_step': cms,
+            'kernel': kernel_name(C['last'][2]),
+            'roofline_frac': gbs / peak, 'kernel_gbs': gbs,
+            'points': len(C['last'][0]) if C['last'][0] is not None else None})
+    # configs[3] at its stated scale: 1 B rows per GPU do not fit in HBM (224
+    # GB), so they are streamed from the pinned pool, cycled; the expected
+    # tallies are the oracle's for the pool, times the cycles
+    stream_leg = None
+    if args.stream_rows > 0:
+        scyc = max(1, args.stream_rows // pool_rows)
+        c4_exp, c4_doc = oracle_tallies('C4', pool_path)
+        barrier()
+        S = one_scan(feed_host_n(scyc), merge=False, q='C4')
+        t = torch.tensor([S[3]], dtype=torch.float64, device='cuda:%d' % dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sms = float(t[0])
+        ok = as_dict(S[0]) == times(c4_exp, scyc) and \
+            S[1]['lines'] == c4_doc['counters']['lines'] * scyc
+        stream_leg = {
+            'config': 'configs[3]: %d rows per GPU streamed from pinned host '
+                      'memory (a %d-row pool cycled %dx), '
+                      '-b latency[aggr=quantize]' %
+                      (scyc * pool_rows, pool_rows, scyc),
+            'value': scyc * pool_rows * world / (sms / 1e3),
+            'unit': 'records/s', 'ms': sms,
+            'h2d_gbs': scyc * pool_len / 1e9 / (sms / 1e3),
+            'parity': 'exact' if ok else 'MISMATCH'}
+
+    # ---- parity on a sample of every rank's shard ---------------------------------
+    srows = min(args.cpu_rows, rows)
+    spath = sample_file(srows, seed, rows)
+    s_exp, s_doc = oracle_tallies(args.query, spath)
+    sample = open(spath, 'rb').read()
+    sbuf = torch.frombuffer(bytearray(sample), dtype=torch.uint8).cuda(dev)
+    g = one_scan(lambda s: s.feed_device(sbuf.data_ptr(), len(sample)),
+                 merge=False)
+    ok = as_dict(g[0]) == s_exp and g[1]['lines'] == s_doc['counters']['lines']
+    # the resident buffer starts with exactly these bytes
+    ok = ok and bytes(buf[:4096].cpu().numpy().tobytes()) == sample[:4096]
+    flags = torch.tensor([1 if ok else 0, 1 if e2e_parity == 'exact' else 0,
+                          1 if (stream_leg is None or
+                                stream_leg['parity'] == 'exact') else 0],
+                         dtype=torch.int32, device='cuda:%d' % dev)
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    parity = 'exact' if int(flags[0]) else 'MISMATCH'
+    e2e_parity = 'exact' if int(flags[1]) else 'MISMATCH'
+    if stream_leg is not None:
+        stream_leg['parity'] = 'exact' if int(flags[2]) else 'MISMATCH'
+
+    # ---- N > 1: the merged tallies must equal the sum of the per-rank ones,
+    # and (oracle) the merged e2e tallies the sum of the ranks' pool tallies ----
     merge_parity = None
     if world > 1:
         local = one_scan(feed_resident, merge=False)[0]
         gathered = [None] * world if rank == 0 else None
-        dist.gather_object(local, gathered, dst=0)
+        dist.gather_object((local, times(pool_exp, cycles)), gathered, dst=0)
         if rank == 0:
-            acc = {}
-            for pts in gathered:
+            acc, exp = {}, {}
+            for pts, pe in gathered:
                 for cols, v in pts:
                     k = tuple(repr(c) for c in cols)
                     acc[k] = acc.get(k, 0) + v
-            got = {tuple(repr(c) for c in cols): v
-                   for cols, v in R['last'][0]}
-            merge_parity = 'exact' if got == acc else 'MISMATCH'
+                for k, v in pe.items():
+                    exp[k] = exp.get(k, 0) + v
+            merge_parity = 'exact' if as_dict(R['last'][0]) == acc and \
+                as_dict(E['last'][0]) == exp else 'MISMATCH'
 
     if rank != 0:
         if comm is not None:
@@ -462,49 +629,35 @@ def gpu_arm(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
 
-    # ---- parity + cpu_baseline on a bounded sample (rank 0, N=1 only) --------------
-    parity = None
+    # ---- cpu_baseline on a bounded sample (rank 0, N=1 only) ---------------------
     cpu = None
     if world == 1 and args.cpu_rows > 0:
-        srows = min(args.cpu_rows, rows)
-        path = sample_file(srows, seed, rows)
-        threads = os.cpu_count() or 1
-        doc = run_oracle(plan, path, threads, repeat=2)
-        sample = open(path, 'rb').read()
-        # the same bytes through the GPU path
-        sbuf = torch.frombuffer(bytearray(sample), dtype=torch.uint8).cuda(dev)
-        g = one_scan(lambda s: s.feed_device(sbuf.data_ptr(), len(sample)),
-                     merge=False)
-        parity = 'exact' if canon(g[0]) == canon(oracle_points(doc)) and \
-            g[1]['lines'] == doc['counters']['lines'] else 'MISMATCH'
-        # the resident buffer starts with exactly these bytes
-        assert bytes(buf[:4096].cpu().numpy().tobytes()) == sample[:4096]
-        cpu = {'value': srows / doc['seconds'], 'unit': 'records/s',
-               'cores': threads, 'kind': 'port',
-               'sample': 'first %d rows (%.2f GB) of the workload, %d '
-                         'threads, best of 2; restated CPU oracle '
-                         '(oracle/dn_oracle.cpp): the reference Node path is '
-                         'not executable here (no node in the image)' %
-                         (srows, len(sample) / 1e9, threads)}
+        cpu, _ = cpu_baseline(plan, srows, rows, seed, os.cpu_count() or 1,
+                              args.cpu_seconds)
 
-    peak, how = measured_peaks()
     n_launch = max(1, R['launches'])
-    # DRAM traffic of the scan kernel comes from a separate `ncu --set full`
-    # capture of this same launch (profiles/): bench.py cannot run under ncu.
+    st = R['last'][2]
+    kname = kernel_name(st)
+    # DRAM traffic of the scan kernel: from the `ncu --set full` capture of
+    # this very command kept in profiles/ (bench.py cannot run under ncu); only
+    # used if it was taken of the kernel this run launched
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    tp = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            traffic = tj['traffic_over_algorithmic'] * \
-                (R['kernel_bytes'] / n_launch)
-            traffic_src = ('dram__bytes_read.sum + dram__bytes_write.sum of '
-                           'the ncu capture in profiles/r1_traffic.json '
-                           '(x%.3f algorithmic)' %
-                           tj['traffic_over_algorithmic'])
+            if tj.get('kernel') == kname.split(' ')[0] and \
+                    tj.get('query') == args.query:
+                traffic = tj['traffic_over_algorithmic'] * \
+                    (R['kernel_bytes'] / n_launch)
+                traffic_src = ('dram__bytes_read.sum + dram__bytes_write.sum '
+                               'of the ncu capture in profiles/r2_traffic.json'
+                               ' (x%.3f algorithmic)' %
+                               tj['traffic_over_algorithmic'])
         except Exception:
             pass
     achieved = (R['kernel_bytes'] / 1e9) / (R['kernel_ms'] / 1e3)
+    h2d_gbs = cycles * pool_len / 1e9 / (e2e_ms / 1e3)
     line = {
         'metric': 'json_records_per_sec', 'value': value,
         'unit': 'records/s', 'n_gpus': world, 'steps': args.steps,
@@ -523,17 +676,24 @@ def gpu_arm(args, rank, local_rank, world):
                   (nbytes / 1e9),
             'points': len(R['last'][0]) if R['last'][0] is not None else None,
             # what the scan specialised itself to from the head of the input
-            'kernel': R['last'][2]['kernel'],
-            'record_templates': R['last'][2]['templates'],
-            'templated_fraction': R['last'][2]['templated_records'] /
+            'kernel': st['kernel'],
+            'record_templates': st['templates'],
+            'templated_fraction': st['templated_records'] /
             max(1, R['last'][1]['lines'] / world),
+            'jit': {'mode': os.environ.get('DNG_JIT'),
+                    'state': st['jit']['state'],
+                    'compile_ms': st['jit']['compile_ms'],
+                    'link_ms': st['jit']['link_ms'],
+                    'error': st['jit']['error'],
+                    'note': 'matcher compiled at run time for the learned '
+                            'templates (NVRTC + nvJitLink), cached per '
+                            'process: compiled once, in the warm-up'},
         },
         'roofline': {
             'bound': 'hbm', 'achieved': achieved, 'peak': peak,
             'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
             'traffic_source': traffic_src,
-            'kernel': 'dng::scan_kernel_w' if R['last'][2]['kernel'] ==
-            'per-warp chunks' else 'dng::scan_kernel',
+            'kernel': kname,
             'bytes_per_launch': R['kernel_bytes'] / n_launch,
             'ms_per_launch': R['kernel_ms'] / n_launch,
             'peak_source': '%s HBM copy bandwidth (MEASURED_PEAKS.json)' % how,
@@ -542,18 +702,28 @@ def gpu_arm(args, rank, local_rank, world):
                 'h2d_bytes_per_step': cycles * pool_len,
                 'd2h_bytes_per_step': result_bytes,
                 'ms_per_step': e2e_ms,
-                'h2d_gbs': cycles * pool_len / 1e9 / (e2e_ms / 1e3),
+                'h2d_gbs': h2d_gbs,
+                'parity': e2e_parity,
+                'roofline': {'bound': 'pcie', 'achieved': h2d_gbs,
+                             'peak': h2d_peak, 'unit': 'GB/s',
+                             'frac': h2d_gbs / h2d_peak,
+                             'peak_source': 'pinned cudaMemcpyAsync H2D of '
+                                            '1 GiB, best of 5, this run'},
                 'note': 'pinned host pool of %d rows fed %dx per step via '
                         'dng_scan_feed_pinned (H2D ring overlapped with the '
-                        'scan kernel)' % (pool_rows, cycles)},
-        # every kernel of ours inside the timed steps: the scan kernel plus
-        # template resolution, newline search and result compaction
+                        'scan kernel); tallies and line count checked against '
+                        'the oracle\'s for the pool x %d' %
+                        (pool_rows, cycles, cycles)},
+        # every kernel of ours inside the timed steps: the scan kernels (+ the
+        # miss kernel of the F path) plus template resolution, newline search
+        # and result compaction
         'gpu_launches': R['all_launches'],
         'scan_kernel_launches': R['launches'],
         'clocks': R['clocks'] if rank == 0 else None,
         'parity': parity,
         'merge_parity': merge_parity,
         'e2e_file': file_leg,
+        'configs': configs + ([stream_leg] if stream_leg else []),
     }
     if cpu:
         line['cpu_baseline'] = cpu
@@ -571,30 +741,39 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--query', default='C2', choices=sorted(QUERIES))
+    ap.add_argument('--query', default='C3', choices=sorted(QUERIES))
     ap.add_argument('--rows', type=int,
                     default=int(os.environ.get('DNG_BENCH_ROWS', 100000000)))
     ap.add_argument('--pool-rows', type=int, default=10000000)
     ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--cfg-steps', type=int, default=2)
+    ap.add_argument('--stream-rows', type=int,
+                    default=int(os.environ.get('DNG_BENCH_STREAM_ROWS',
+                                               1000000000)))
     ap.add_argument('--cpu-rows', type=int, default=4000000)
+    ap.add_argument('--cpu-seconds', type=float, default=4.0)
     ap.add_argument('--file-steps', type=int, default=2)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        # the oracle only: the product library is not even looked for
+        reference_arm(args, rank, world)
+        return 0
     import __graft_entry__
-    from dragnet_b200 import native
+    lib_path = os.path.join(ROOT, 'dragnet_b200', 'libdragnet_gpu.so')
     oexe = os.path.join(ROOT, 'oracle', 'dn_oracle_cpp')
+    ogen = os.path.join(ROOT, 'oracle', 'gen_ndjson')
     if rank == 0:
-        if not (os.path.exists(native.LIB_PATH) and os.path.exists(oexe)):
+        if not (os.path.exists(lib_path) and os.path.exists(oexe) and
+                os.path.exists(ogen)):
             __graft_entry__.build()
     else:
         t0 = time.time()
-        while not os.path.exists(native.LIB_PATH) and time.time() - t0 < 600:
+        while not (os.path.exists(lib_path) and os.path.exists(ogen)) and \
+                time.time() - t0 < 600:
             time.sleep(1)
-    if args.impl == 'reference':
-        reference_arm(args, rank, world)
-        return 0
     gpu_arm(args, rank, local_rank, world)
     return 0
 

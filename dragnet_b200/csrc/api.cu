@@ -1319,6 +1319,23 @@ int dng_scan_feed_device(dng_scan *s, const void *devbuf, size_t len)
 		    "aligned");
 	if (len == 0)
 		return 0;
+	/*
+	 * A CTA's tally cache counts in 32 bits and is flushed once per launch.
+	 * With weight-1 records that cannot wrap within a launch over any buffer
+	 * HBM holds; with json-skinner weights (up to 255 take the cache) a
+	 * launch is kept to 4 GiB: 29 MB per CTA, under 2^32 / 255 records of
+	 * even the shortest point line.
+	 */
+	const size_t LAUNCH_MAX = (size_t)4 << 30;
+	if (s->plan.dev.format == FMT_SKINNER && len > LAUNCH_MAX) {
+		for (size_t off = 0; off < len; off += LAUNCH_MAX) {
+			int rc = dng_scan_feed_device(s, (const u8 *)devbuf + off,
+			    std::min(LAUNCH_MAX, len - off));
+			if (rc)
+				return rc;
+		}
+		return 0;
+	}
 	cudaSetDevice(s->device);
 	const u8 *d = (const u8 *)devbuf;
 	s->bytes_fed += len;
@@ -1536,8 +1553,10 @@ int dng_scan_finish(dng_scan *s, dng_result **out)
 		return s->fail(DNG_EUNSUPPORTED, "input contains records the "
 		    "device path cannot decide yet (" +
 		    std::to_string(c.unsupported) + "): nesting deeper than 64, "
-		    "a group key longer than 512 bytes, a line >= 16 MiB, or "
-		    "an array where an index/length lookup is needed");
+		    "a group key longer than 512 bytes, a line >= 16 MiB, an "
+		    "array where an index/length lookup is needed, or a date "
+		    "string outside the ISO format (V8's legacy Date.parse "
+		    "forms are not restated)");
 	u32 n = misc[1];
 	dng_result *r = new dng_result();
 	r->init_from_plan(&s->plan);

@@ -275,10 +275,7 @@ DNG_HD bool fdate(M &m, u32 off, u32 n, int64_t *ms)
 			const int msec = DNG_D(w5, 0) * 100 + DNG_D(w5, 1) * 10 +
 			    DNG_D(w5, 2);
 #undef DNG_D
-			const int leap = (y % 4 == 0) && (y % 100 != 0 || y % 400 == 0);
-			const int dim = mo == 2 ? (leap ? 29 : 28) :
-			    (mo == 4 || mo == 6 || mo == 9 || mo == 11) ? 30 : 31;
-			if (mo >= 1 && mo <= 12 && dd >= 1 && dd <= dim &&
+			if (mo >= 1 && mo <= 12 && dd >= 1 && dd <= 31 &&
 			    hh <= 23 && mi <= 59 && ss <= 59) {
 				*ms = (int64_t)days_from_civil(y, mo, dd) *
 				    86400000ll + (int64_t)(((hh * 60 + mi) * 60 +
@@ -328,8 +325,11 @@ DNG_HD u32 fstage(M &m, const FPlan &F, u32 defmask, double &s0, double &s1)
 						if (fdate(m, fcap_off(cw), fcap_len(cw),
 						    &ms))
 							v = floor((double)ms / 1000.0);
-						else
+						else if (dng_date_hopeless(m.ptr(
+						    fcap_off(cw)), (int)fcap_len(cw)))
 							e = FO_SYNTH_BADDATE;
+						else
+							return FO_MISS;	/* (jsdate.cuh) */
 					} else if (t == T_OBJ || t == T_ARR) {
 						return FO_MISS;
 					} else {

@@ -30,6 +30,8 @@
 #ifndef DNG_FAST_KERNEL_CUH
 #define DNG_FAST_KERNEL_CUH
 
+#include <stddef.h>
+
 #include "scan_kernel.cuh"
 #include "fast.cuh"
 
@@ -164,7 +166,26 @@ __device__ __noinline__ void fslow_add(FSmem m, const FPlan *F, u32 defmask,
 	shared_add(stab, *gt, key_hash_words(kw, klen), kw, klen, 1);
 }
 
-/* count the record's key: the CTA's inline tier, probed with the F hash */
+__device__ __forceinline__ unsigned long long lds64_acquire(u32 addr)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr)
+	    : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void sts64_release(u32 addr, unsigned long long v)
+{
+	asm volatile("st.release.cta.shared.u64 [%0], %1;" :: "r"(addr), "l"(v)
+	    : "memory");
+}
+
+/*
+ * Count the record's key: the CTA's inline tier, probed with the F hash.  A
+ * slot's tag is published with release semantics once its key is written and
+ * read with acquire semantics (plain shared loads and stores in SASS: no
+ * fence on the path every record takes).
+ */
 __device__ __forceinline__ void ftally(FSmem &m, const FPlan &F, u32 defmask,
     u32 h, u32 klen, const STab &stab, const GTable &gt)
 {
@@ -173,8 +194,8 @@ __device__ __forceinline__ void ftally(FSmem &m, const FPlan &F, u32 defmask,
 		u32 idx = (h >> 7) & stab.mask1;
 		for (u32 probe = 0; probe < 8; probe++) {
 			SSlot1 *s = &stab.s1[idx];
-			unsigned long long tag =
-			    *(volatile unsigned long long *)&s->tag;
+			const u32 sa = smem_u32(s);
+			unsigned long long tag = lds64_acquire(sa);
 			if (tag == 0) {
 				const unsigned long long old =
 				    atomicCAS(&s->tag, 0ull, claim);
@@ -182,20 +203,17 @@ __device__ __forceinline__ void ftally(FSmem &m, const FPlan &F, u32 defmask,
 					s->klen = klen;
 					fkey_write(m, F, defmask, (u8 *)s->key);
 					atomicAdd(&s->count, 1u);
-					__threadfence_block();
-					*(volatile unsigned long long *)&s->tag =
-					    claim | DNG_READY;
+					sts64_release(sa, claim | DNG_READY);
 					return;
 				}
 				tag = old;
 			}
 			if ((tag & ~DNG_READY) == claim) {
 				while (!(tag & DNG_READY))
-					tag = *(volatile unsigned long long *)&s->tag;
-				__threadfence_block();
-				if (*(volatile u32 *)&s->klen == klen) {
+					tag = lds64_acquire(sa);
+				if (lds32(sa + (u32)offsetof(SSlot1, klen)) == klen) {
 					FKeySmem k;
-					k.ka = smem_u32(s->key);
+					k.ka = sa + (u32)offsetof(SSlot1, key);
 					if (fkey_equal(m, F, defmask, k)) {
 						atomicAdd(&s->count, 1u);
 						return;

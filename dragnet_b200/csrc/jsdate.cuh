@@ -5,8 +5,16 @@
  *
  * Grammar: YYYY | YYYY-MM | YYYY-MM-DD | +-YYYYYY-..., optionally followed by
  * THH:mm | THH:mm:ss | THH:mm:ss.s+ and optionally Z | +-HH:mm.  No offset
- * means UTC.  Anything else is NaN (the reference then counts `baddate`).
- * V8's legacy free-form fallback is not restated (unpinned).
+ * means UTC.  A day of 29..31 in a shorter month carries into the next one,
+ * as V8's parser lets it (its day check is 1..31; MakeDay does the rest).
+ *
+ * V8 falls back to a legacy free-form parser for everything else ("May 1,
+ * 2014", "2014-05-01 12:00:00", RFC 2822 ...), which is not restated here.
+ * So a string that is not in the grammar is only CALLED NaN (the reference
+ * then counts `baddate`) when no date parser could make anything of it: when
+ * it holds no digit at all (dng_date_hopeless).  Any other string makes the
+ * scan fail loudly (the `unsupported` counter -> DNG_EUNSUPPORTED) instead of
+ * silently dropping records the reference would have kept.
  */
 #ifndef DNG_JSDATE_CUH
 #define DNG_JSDATE_CUH
@@ -112,12 +120,7 @@ DNG_HDN bool dng_date_parse(const uint8_t *p, int n, int64_t *ms)
 	}
 	if (i != n)
 		return false;
-	if (mo < 1 || mo > 12 || dd < 1)
-		return false;
-	int leap = (y % 4 == 0) && (y % 100 != 0 || y % 400 == 0);
-	int dim = mo == 2 ? (leap ? 29 : 28) :
-	    (mo == 4 || mo == 6 || mo == 9 || mo == 11) ? 30 : 31;
-	if (dd > dim)
+	if (mo < 1 || mo > 12 || dd < 1 || dd > 31)
 		return false;
 	if (hh > 24 || mi > 59 || ss > 59)
 		return false;
@@ -128,6 +131,15 @@ DNG_HDN bool dng_date_parse(const uint8_t *p, int n, int64_t *ms)
 	if (t > 8640000000000000ll || t < -8640000000000000ll)
 		return false;
 	*ms = t;
+	return true;
+}
+
+/* a string no date parser makes a date of: it has no digit */
+DNG_HD bool dng_date_hopeless(const uint8_t *p, int n)
+{
+	for (int i = 0; i < n; i++)
+		if (p[i] >= '0' && p[i] <= '9')
+			return false;
 	return true;
 }
 

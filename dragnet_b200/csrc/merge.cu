@@ -292,6 +292,10 @@ struct dng_comm {
 	nccl_comm comm = nullptr;
 	int nranks = 1, rank = 0, device = 0;
 	cudaStream_t stream = nullptr;
+	/* allocated with the communicator, so that the agreement rounds of a
+	 * merge never depend on an allocation succeeding: 2 x (nranks + 1)
+	 * 64-bit words on the device, as many pinned on the host */
+	unsigned long long *d_hdr = nullptr, *h_hdr = nullptr;
 };
 
 extern "C" {
@@ -335,7 +339,16 @@ int dng_comm_init(dng_comm **out, int nranks, int rank, const void *id128,
 		delete c;
 		return DNG_ENCCL;
 	}
-	cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	const size_t hb = 2 * ((size_t)nranks + 1) * sizeof (unsigned long long);
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) !=
+	    cudaSuccess || cudaMalloc((void **)&c->d_hdr, hb) != cudaSuccess ||
+	    cudaMallocHost((void **)&c->h_hdr, hb) != cudaSuccess) {
+		if (err && errlen)
+			snprintf(err, errlen, "communicator scratch: %s",
+			    cudaGetErrorString(cudaGetLastError()));
+		dng_comm_destroy(c);
+		return DNG_ECUDA;
+	}
 	*out = c;
 	return DNG_OK;
 }
@@ -349,7 +362,47 @@ void dng_comm_destroy(dng_comm *c)
 		nccl().CommDestroy(c->comm);
 	if (c->stream)
 		cudaStreamDestroy(c->stream);
+	if (c->d_hdr)
+		cudaFree(c->d_hdr);
+	if (c->h_hdr)
+		cudaFreeHost(c->h_hdr);
 	delete c;
+}
+
+/*
+ * Every rank tells every rank a (size, status) pair: one all-gather over the
+ * communicator's own scratch.  Returns this rank's status if it is non-zero,
+ * else the first non-zero status of a peer, else 0 -- the SAME verdict
+ * (zero or not) on every rank, so that all of them go on to the next
+ * collective or none does.  DNG_ENCCL if the collective itself failed (then
+ * nothing more can be agreed on).  sizes (nranks) may be null.
+ */
+static int merge_agree(dng_comm *c, unsigned long long size, int status,
+    unsigned long long *sizes)
+{
+	NcclApi &n = nccl();
+	const int R = c->nranks;
+	unsigned long long *h = c->h_hdr;
+	h[2 * R] = size;
+	h[2 * R + 1] = (unsigned long long)(long long)status;
+	if (cudaMemcpyAsync(c->d_hdr + 2 * R, h + 2 * R, 16,
+	    cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+		return DNG_ECUDA;	/* (the copy engine is gone: so is NCCL) */
+	if (n.AllGather(c->d_hdr + 2 * R, c->d_hdr, 16, NCCL_UINT8, c->comm,
+	    c->stream) != 0)
+		return DNG_ENCCL;
+	if (cudaMemcpyAsync(h, c->d_hdr, 16 * (size_t)R, cudaMemcpyDeviceToHost,
+	    c->stream) != cudaSuccess ||
+	    cudaStreamSynchronize(c->stream) != cudaSuccess)
+		return DNG_ECUDA;
+	int peer = 0;
+	for (int i = 0; i < R; i++) {
+		if (sizes)
+			sizes[i] = h[2 * i];
+		if (!peer && h[2 * i + 1] != 0)
+			peer = (int)(long long)h[2 * i + 1];
+	}
+	return status ? status : peer;
 }
 
 int dng_merge_nccl(dng_scan *scan, dng_comm *c, int root, dng_result **out,
@@ -359,97 +412,137 @@ int dng_merge_nccl(dng_scan *scan, dng_comm *c, int root, dng_result **out,
 		return DNG_EINVAL;
 	NcclApi &n = nccl();
 	*out = nullptr;
+	const int R = c->nranks;
+	/*
+	 * A failure on one rank (a full table, an unsupported record, a CUDA
+	 * error, an allocation) must not leave its peers blocked in a
+	 * collective it never enters: before each data collective the ranks
+	 * exchange their status, and either all go on or all return.
+	 */
 	dng_result *local = nullptr;
-	int rc = dng_scan_finish(scan, &local);
-	if (rc)
-		return rc;
 	dng_counters lc;
-	rc = dng_scan_counters(scan, &lc);
-	if (rc) {
-		dng_result_destroy(local);
-		return rc;
-	}
-	cudaSetDevice(c->device);
-	const void *dict;
-	size_t dlen;
-	dng_result_dict(local, &dict, &dlen);
+	memset(&lc, 0, sizeof (lc));
+	int st = dng_scan_finish(scan, &local);
+	if (!st)
+		st = dng_scan_counters(scan, &lc);
+	if (cudaSetDevice(c->device) != cudaSuccess && !st)
+		st = DNG_ECUDA;
+	const void *dict = nullptr;
+	size_t dlen = 0;
+	if (!st)
+		dng_result_dict(local, &dict, &dlen);
 
-	/* (a) all-gather dictionary sizes, then the padded dictionaries */
-	unsigned long long *d_sz = nullptr;
-	dng_cached_alloc(c->device, (void **)&d_sz, 4096);
-	unsigned long long mysz = dlen;
-	cudaMemcpyAsync(d_sz + c->nranks, &mysz, 8, cudaMemcpyHostToDevice,
-	    c->stream);
-	int nrc = n.AllGather(d_sz + c->nranks, d_sz, 8, NCCL_UINT8, c->comm,
-	    c->stream);
-	std::vector<unsigned long long> sizes(c->nranks);
-	cudaMemcpyAsync(sizes.data(), d_sz, 8 * c->nranks,
-	    cudaMemcpyDeviceToHost, c->stream);
-	cudaStreamSynchronize(c->stream);
-	size_t maxsz = 16;
+	unsigned char *d_all = nullptr, *d_mine = nullptr;
+	uint64_t *d_vec = nullptr, *d_red = nullptr;
+	void *gdict = nullptr;
+	size_t glen = 0;
+	std::vector<unsigned long long> sizes(R);
+	std::vector<unsigned char> all;
+	std::vector<uint64_t> vec;
+	const size_t NC = sizeof (dng_counters) / sizeof (uint64_t);
+	size_t G = 0, maxsz = 16;
+	int rc;
+
+	/* (a) dictionary sizes + status of the local scans */
+	rc = merge_agree(c, dlen, st, sizes.data());
+	if (rc)
+		goto done;
 	for (auto v : sizes)
 		maxsz = std::max(maxsz, (size_t)v);
 	maxsz = (maxsz + 15) & ~(size_t)15;
-	unsigned char *d_all = nullptr, *d_mine = nullptr;
-	dng_cached_alloc(c->device, (void **)&d_all,
-	    pow2_at_least(maxsz * c->nranks));
-	dng_cached_alloc(c->device, (void **)&d_mine, pow2_at_least(maxsz));
-	cudaMemsetAsync(d_mine, 0, maxsz, c->stream);
-	cudaMemcpyAsync(d_mine, dict, dlen, cudaMemcpyHostToDevice, c->stream);
-	if (!nrc)
-		nrc = n.AllGather(d_mine, d_all, maxsz, NCCL_UINT8, c->comm,
-		    c->stream);
-	std::vector<unsigned char> all(maxsz * c->nranks);
-	cudaMemcpyAsync(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost,
-	    c->stream);
-	cudaStreamSynchronize(c->stream);
-	std::vector<const void *> bufs(c->nranks);
-	std::vector<size_t> lens(c->nranks);
-	for (int i = 0; i < c->nranks; i++) {
-		bufs[i] = all.data() + (size_t)i * maxsz;
-		lens[i] = (size_t)sizes[i];
+	if (dng_cached_alloc(c->device, (void **)&d_all,
+	    pow2_at_least(maxsz * R)) != cudaSuccess ||
+	    dng_cached_alloc(c->device, (void **)&d_mine,
+	    pow2_at_least(maxsz)) != cudaSuccess)
+		st = DNG_ENOMEM;
+	try {
+		all.resize(maxsz * R);
+	} catch (...) {
+		st = DNG_ENOMEM;
 	}
-	void *gdict = nullptr;
-	size_t glen = 0;
-	if (!nrc)
-		rc = dng_dict_union(bufs.data(), lens.data(), c->nranks, &gdict,
-		    &glen);
+	if (!st && (cudaMemsetAsync(d_mine, 0, maxsz, c->stream) != cudaSuccess ||
+	    cudaMemcpyAsync(d_mine, dict, dlen, cudaMemcpyHostToDevice,
+	    c->stream) != cudaSuccess))
+		st = DNG_ECUDA;
+	rc = merge_agree(c, 0, st, nullptr);
+	if (rc)
+		goto done;
 
-	/* (b) dense tallies (+ counters) and the single sum-reduce */
-	size_t G = rc || nrc ? 0 : dng_dict_count(gdict, glen);
-	const size_t NC = sizeof (dng_counters) / sizeof (uint64_t);
-	std::vector<uint64_t> vec(G + NC);
-	if (!rc && !nrc)
-		rc = dng_result_dense(local, gdict, glen, vec.data(), G);
-	memcpy(vec.data() + G, &lc, sizeof (lc));
-	uint64_t *d_vec = nullptr, *d_red = nullptr;
-	dng_cached_alloc(c->device, (void **)&d_vec, pow2_at_least(vec.size() * 8));
-	dng_cached_alloc(c->device, (void **)&d_red, pow2_at_least(vec.size() * 8));
-	cudaMemcpyAsync(d_vec, vec.data(), vec.size() * 8,
-	    cudaMemcpyHostToDevice, c->stream);
-	if (!rc && !nrc)
-		nrc = n.Reduce(d_vec, d_red, vec.size(), NCCL_UINT64, NCCL_SUM,
-		    root, c->comm, c->stream);
-	if (!rc && !nrc && c->rank == root) {
-		cudaMemcpyAsync(vec.data(), d_red, vec.size() * 8,
-		    cudaMemcpyDeviceToHost, c->stream);
-		cudaStreamSynchronize(c->stream);
+	/* (b) the padded dictionaries */
+	if (n.AllGather(d_mine, d_all, maxsz, NCCL_UINT8, c->comm, c->stream)) {
+		rc = DNG_ENCCL;
+		goto done;
+	}
+	if (cudaMemcpyAsync(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost,
+	    c->stream) != cudaSuccess ||
+	    cudaStreamSynchronize(c->stream) != cudaSuccess)
+		st = DNG_ECUDA;
+	if (!st) {
+		std::vector<const void *> bufs(R);
+		std::vector<size_t> lens(R);
+		for (int i = 0; i < R; i++) {
+			bufs[i] = all.data() + (size_t)i * maxsz;
+			lens[i] = (size_t)sizes[i];
+		}
+		st = dng_dict_union(bufs.data(), lens.data(), R, &gdict, &glen);
+	}
+	/* (c) dense tallies (+ counters): same length on every rank */
+	if (!st) {
+		G = dng_dict_count(gdict, glen);
+		try {
+			vec.resize(G + NC);
+		} catch (...) {
+			st = DNG_ENOMEM;
+		}
+	}
+	if (!st)
+		st = dng_result_dense(local, gdict, glen, vec.data(), G);
+	if (!st) {
+		memcpy(vec.data() + G, &lc, sizeof (lc));
+		if (dng_cached_alloc(c->device, (void **)&d_vec,
+		    pow2_at_least(vec.size() * 8)) != cudaSuccess ||
+		    dng_cached_alloc(c->device, (void **)&d_red,
+		    pow2_at_least(vec.size() * 8)) != cudaSuccess)
+			st = DNG_ENOMEM;
+		else if (cudaMemcpyAsync(d_vec, vec.data(), vec.size() * 8,
+		    cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+			st = DNG_ECUDA;
+	}
+	rc = merge_agree(c, G, st, sizes.data());
+	if (!rc)
+		for (auto v : sizes)
+			if (v != G)
+				rc = DNG_ENCCL;	/* (cannot happen: same inputs) */
+	if (rc)
+		goto done;
+
+	/* (d) the single sum-reduce */
+	if (n.Reduce(d_vec, d_red, vec.size(), NCCL_UINT64, NCCL_SUM, root,
+	    c->comm, c->stream)) {
+		rc = DNG_ENCCL;
+		goto done;
+	}
+	if (c->rank == root) {
+		if (cudaMemcpyAsync(vec.data(), d_red, vec.size() * 8,
+		    cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+		    cudaStreamSynchronize(c->stream) != cudaSuccess) {
+			rc = DNG_ECUDA;
+			goto done;
+		}
 		rc = dng_result_from_dense(local, gdict, glen, vec.data(), G,
 		    out);
-		if (counters)
+		if (!rc && counters)
 			memcpy(counters, vec.data() + G, sizeof (*counters));
-	} else {
-		cudaStreamSynchronize(c->stream);
+	} else if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+		rc = DNG_ECUDA;
 	}
-	dng_cached_free(d_sz);
+done:
 	dng_cached_free(d_all);
 	dng_cached_free(d_mine);
 	dng_cached_free(d_vec);
 	dng_cached_free(d_red);
 	dng_buf_free(gdict);
 	dng_result_destroy(local);
-	if (nrc)
-		return DNG_ENCCL;
 	return rc;
 }
 

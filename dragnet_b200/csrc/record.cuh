@@ -1134,11 +1134,18 @@ DNG_HD int process_metric(const u8 *rec, const DevPlan &P, u32 mi, RecState &R,
 			if (t == T_STR && !(val_flags(v.pk) & VF_ESCAPED)) {
 				ok = dng_date_parse(rec + val_off(v.pk),
 				    (int)val_len(v.pk), &ms);
+				/* (not ISO, but V8's legacy parser might know it:
+				 * not ours to call NaN, jsdate.cuh) */
+				if (!ok && !dng_date_hopeless(rec + val_off(v.pk),
+				    (int)val_len(v.pk)))
+					ovf = 1;
 			} else if (t == T_STR || t == T_ARR) {
 				u32 o = 0;
 				value_to_string(rec, v, kbuf, o, KEY_MAX, ovf,
 				    slow);
 				ok = dng_date_parse(kbuf, (int)o, &ms);
+				if (!ok && !dng_date_hopeless(kbuf, (int)o))
+					ovf = 1;
 			}
 			if (!ok) {
 				if (!nerr)

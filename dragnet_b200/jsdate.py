@@ -46,7 +46,8 @@ def date_parse_ms(s):
     y = int(ys)
     mo = int(mo) if mo else 1
     dd = int(dd) if dd else 1
-    if not (1 <= mo <= 12) or not (1 <= dd <= _dim(y, mo)):
+    # (V8 accepts day 1..31 in any month and lets it carry over)
+    if not (1 <= mo <= 12) or not (1 <= dd <= 31):
         return None
     h = int(hh) if hh else 0
     mi_ = int(mi) if mi else 0

@@ -120,7 +120,10 @@ int dng_scan_set_stream(dng_scan *scan, void *cuda_stream);
  *   cudaHostRegister'd); DMA'd directly; the buffer must stay valid and
  *   unmodified until the next dng_scan_sync()/dng_scan_finish().
  * dng_scan_feed_device: bytes already resident in this device's HBM
- *   (16-byte aligned); scanned in place, no copy.
+ *   (16-byte aligned); scanned in place, no copy.  The kernels that read the
+ *   buffer are only ENQUEUED when this returns (on the scan's stream, or the
+ *   caller's after dng_scan_set_stream): like a pinned buffer, it must stay
+ *   valid and unmodified until the next dng_scan_sync()/dng_scan_finish().
  * dng_scan_feed_file: read(2) the file into the pinned ring and feed it.
  */
 int dng_scan_feed(dng_scan *scan, const void *buf, size_t len);

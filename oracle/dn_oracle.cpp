@@ -749,9 +749,8 @@ bool date_parse(const std::string &s, int64_t &ms)
 	}
 	if (i != n)
 		return false;
-	bool leap = (y % 4 == 0) && (y % 100 != 0 || y % 400 == 0);
-	int dim[] = { 31, leap ? 29 : 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31 };
-	if (mo < 1 || mo > 12 || d < 1 || d > dim[mo - 1])
+	/* (V8 takes any day 1..31 and lets MakeDay carry it over) */
+	if (mo < 1 || mo > 12 || d < 1 || d > 31)
 		return false;
 	if (hh > 24 || mi > 59 || ss > 59 || (hh == 24 && (mi || ss || msec)))
 		return false;
@@ -933,7 +932,17 @@ void scan_line(const Plan &pl, const unsigned char *s, size_t n, Tally &T)
 				out = v;
 			} else {
 				int64_t ms;
-				if (!date_parse(to_string(v), ms)) {
+				const std::string text = to_string(v);
+				if (!date_parse(text, ms) && text.find_first_of(
+				    "0123456789") != std::string::npos) {
+					/* V8's legacy parser may know it: not
+					 * restated, not ours to call NaN */
+					fprintf(stderr, "dn_oracle: unsupported: "
+					    "Date.parse(\"%s\") outside the ISO "
+					    "format\n", text.c_str());
+					exit(3);
+				}
+				if (!date_parse(text, ms)) {
 					if (!nerr)
 						T.c.synth_baddate++;
 					nerr++;
@@ -1018,7 +1027,7 @@ int main(int argc, char **argv)
 {
 	if (argc < 2) {
 		fprintf(stderr, "usage: dn_oracle PLAN.json [--threads N] "
-		    "[--repeat R] FILE...\n");
+		    "[--repeat R] [--min-seconds S] FILE...\n");
 		return 2;
 	}
 	std::ifstream pf(argv[1], std::ios::binary);
@@ -1030,12 +1039,17 @@ int main(int argc, char **argv)
 		return 1;
 	}
 	int threads = 1, repeat = 1;
+	double min_seconds = 0;
 	std::string data;
 	for (int i = 2; i < argc; i++) {
 		if (!strcmp(argv[i], "--threads") && i + 1 < argc) {
 			threads = atoi(argv[++i]);
 		} else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) {
 			repeat = atoi(argv[++i]);
+		} else if (!strcmp(argv[i], "--min-seconds") && i + 1 < argc) {
+			/* keep scanning until this much time has been measured
+			 * (bench.py: a step long enough to be stable) */
+			min_seconds = atof(argv[++i]);
 		} else {
 			std::ifstream f(argv[i], std::ios::binary);
 			std::stringstream ss;
@@ -1048,8 +1062,9 @@ int main(int argc, char **argv)
 	const unsigned char *d = (const unsigned char *)data.data();
 	size_t total = data.size();
 	Tally result;
-	double best = 1e300;
-	for (int rep = 0; rep < repeat; rep++) {
+	double best = 1e300, spent = 0;
+	int reps = 0;
+	for (int rep = 0; rep < repeat || spent < min_seconds; rep++) {
 		auto t0 = std::chrono::steady_clock::now();
 		std::vector<Tally> parts(threads);
 		std::vector<std::thread> th;
@@ -1069,8 +1084,10 @@ int main(int argc, char **argv)
 			merged.c.add(p.c);
 		}
 		auto t1 = std::chrono::steady_clock::now();
-		best = std::min(best,
-		    std::chrono::duration<double>(t1 - t0).count());
+		const double dt = std::chrono::duration<double>(t1 - t0).count();
+		best = std::min(best, dt);
+		spent += dt;
+		reps++;
 		result = std::move(merged);
 	}
 	if (pl.bds.empty()) {
@@ -1108,7 +1125,8 @@ int main(int argc, char **argv)
 	    "\"user_filtered\":%llu,\"user_failedeval\":%llu,\"synth_undef\":%llu,"
 	    "\"synth_baddate\":%llu,\"time_filtered\":%llu,"
 	    "\"time_failedeval\":%llu,\"aggr\":%llu,\"unsupported\":0},"
-	    "\"seconds\":%.6f,\"threads\":%d,\"bytes\":%llu}\n",
+	    "\"seconds\":%.6f,\"mean_seconds\":%.6f,\"reps\":%d,"
+	    "\"threads\":%d,\"bytes\":%llu}\n",
 	    (unsigned long long)c.lines, (unsigned long long)c.invalid_json,
 	    (unsigned long long)c.invalid_point,
 	    (unsigned long long)c.ds_filtered,
@@ -1119,6 +1137,7 @@ int main(int argc, char **argv)
 	    (unsigned long long)c.synth_baddate,
 	    (unsigned long long)c.time_filtered,
 	    (unsigned long long)c.time_failedeval, (unsigned long long)c.aggr,
-	    best, threads, (unsigned long long)total);
+	    best, spent / (reps ? reps : 1), reps, threads,
+	    (unsigned long long)total);
 	return 0;
 }

@@ -348,6 +348,10 @@ def _days_from_civil(y, m, d):
     return era * 146097 + doe - 719468
 
 
+class Unsupported(Exception):
+    """Input whose reference behaviour this restatement does not cover."""
+
+
 def date_parse_ms(b):
     m = _ISO.match(b)
     if not m:
@@ -358,9 +362,8 @@ def date_parse_ms(b):
     y = int(ys)
     mo = int(mo) if mo else 1
     dd = int(dd) if dd else 1
-    leap = y % 4 == 0 and (y % 100 != 0 or y % 400 == 0)
-    dim = [31, 29 if leap else 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
-    if not (1 <= mo <= 12) or not (1 <= dd <= dim[mo - 1]):
+    # V8's parser takes any day 1..31 and lets MakeDay carry it over
+    if not (1 <= mo <= 12) or not (1 <= dd <= 31):
         return None
     h = int(hh) if hh else 0
     mn = int(mi) if mi else 0
@@ -520,7 +523,14 @@ def scan(plan, chunks):
                 if isinstance(val, float):
                     parsed = val
                 else:
-                    ms = date_parse_ms(js_to_string(val))
+                    text = js_to_string(val)
+                    ms = date_parse_ms(text)
+                    if ms is None and any(48 <= c <= 57 for c in text):
+                        # not in the ES5 format, but V8's legacy parser may
+                        # well make a date of it: not restated, so not ours
+                        # to call NaN (the CUDA path refuses such input too)
+                        raise Unsupported('Date.parse(%r): outside the '
+                                          'ISO format' % text)
                     if ms is None:
                         if nerrors == 0:
                             _bump(counters, 'Datetime parser', 'baddate')

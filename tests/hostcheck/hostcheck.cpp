@@ -48,7 +48,7 @@ static std::string slurp(const char *path)
 static const char *HOST_PRELUDE =
 "#include <stdint.h>\n#include <string.h>\n"
 "typedef uint8_t u8; typedef uint32_t u32; typedef uint64_t u64;\n"
-"#define DNG_HD static inline\n#define __device__\n"
+"#define DNG_HD static inline\n#define __device__\n#define __syncwarp()\n"
 "enum { T_UNDEF = 0, T_NULL = 1, T_FALSE = 2, T_TRUE = 3, T_NUM = 4, T_STR = 5 };\n"
 "#define DNG_FCAP(type, off, len, flag) \\\n"
 "	((u32)(off) | ((u32)(len) << 12) | ((u32)(type) << 24) | ((u32)(flag) << 27))\n"

@@ -97,3 +97,40 @@ def test_template_fuzz(seed, tmp_path):
     path = _write(tmp_path, 'fz.log', corpus.template_fuzz_lines(seed, 800))
     for argv, ds in corpus.EDGE_QUERIES[:30:4]:
         _compare(corpus.make_plan(argv, ds), path)
+
+
+def test_legacy_date_strings_are_refused_not_dropped(tmp_path):
+    """A date string outside the ES5 format that V8's legacy Date.parse might
+    accept is neither parsed nor called NaN: the device code flags the record
+    unsupported (the scan then fails with DNG_EUNSUPPORTED) and the oracle
+    raises; a string without any digit is NaN (`baddate`) in both."""
+    import json
+    import subprocess
+    import dn_oracle
+    from engines import build_hostcheck
+    lines = [b'{"time":"2014-05-01T00:00:00Z","a":1}',
+             b'{"time":"nonsense","a":1}']
+    plan = corpus.make_plan(
+        ['-b', 'ts[date,field=time,aggr=lquantize,step=86400]'])
+    p = tmp_path / 'ok.log'
+    p.write_bytes(b'\n'.join(lines) + b'\n')
+    _compare(plan, str(p))
+    for bad in (b'Thu, 01 May 2014 00:00:00 GMT', b'2014-05-01 12:00:00',
+                b'May 1, 2014', b'2014-13-45'):
+        q = tmp_path / 'bad.log'
+        q.write_bytes(b'\n'.join(lines + [b'{"time":"' + bad + b'"}']) + b'\n')
+        with pytest.raises(dn_oracle.Unsupported):
+            py_engine(plan, [str(q)])
+        pf = tmp_path / 'plan.json'
+        pf.write_text(json.dumps(plan))
+        out = subprocess.run([build_hostcheck(), str(pf), str(q)],
+                             capture_output=True, env=dict(os.environ),
+                             check=True).stdout
+        assert json.loads(out)['counters']['unsupported'] == 1, bad
+    # day 30 of February carries over (V8), it is not NaN
+    r = tmp_path / 'feb.log'
+    r.write_bytes(b'{"time":"2014-02-30T00:00:00Z"}\n'
+                  b'{"time":"2014-03-02T00:00:00Z"}\n')
+    exp_p, _ = py_engine(plan, [str(r)])
+    assert [v for _, v in exp_p] == [2]
+    _compare(plan, str(r))
