@@ -325,11 +325,11 @@ DNG_HD u32 fstage(M &m, const FPlan &F, u32 defmask, double &s0, double &s1)
 						if (fdate(m, fcap_off(cw), fcap_len(cw),
 						    &ms))
 							v = floor((double)ms / 1000.0);
-						else if (dng_date_hopeless(m.ptr(
+						else if (dng_date_maybe_legacy(m.ptr(
 						    fcap_off(cw)), (int)fcap_len(cw)))
-							e = FO_SYNTH_BADDATE;
-						else
 							return FO_MISS;	/* (jsdate.cuh) */
+						else
+							e = FO_SYNTH_BADDATE;
 					} else if (t == T_OBJ || t == T_ARR) {
 						return FO_MISS;
 					} else {

@@ -10,11 +10,11 @@
  *
  * V8 falls back to a legacy free-form parser for everything else ("May 1,
  * 2014", "2014-05-01 12:00:00", RFC 2822 ...), which is not restated here.
- * So a string that is not in the grammar is only CALLED NaN (the reference
- * then counts `baddate`) when no date parser could make anything of it: when
- * it holds no digit at all (dng_date_hopeless).  Any other string makes the
- * scan fail loudly (the `unsupported` counter -> DNG_EUNSUPPORTED) instead of
- * silently dropping records the reference would have kept.
+ * A string that is not in the grammar is called NaN (the reference then counts
+ * `baddate`) unless it looks like one of the forms that legacy parser exists
+ * for (dng_date_maybe_legacy): such a string makes the scan fail loudly (the
+ * `unsupported` counter -> DNG_EUNSUPPORTED) instead of silently dropping
+ * records the reference may have kept.
  */
 #ifndef DNG_JSDATE_CUH
 #define DNG_JSDATE_CUH
@@ -134,13 +134,38 @@ DNG_HDN bool dng_date_parse(const uint8_t *p, int n, int64_t *ms)
 	return true;
 }
 
-/* a string no date parser makes a date of: it has no digit */
-DNG_HD bool dng_date_hopeless(const uint8_t *p, int n)
+/*
+ * Could V8's legacy parser make a date of this (non-ISO) string?  Not decided
+ * here -- only whether it LOOKS like one of the forms that parser exists for:
+ * a month name, two date separators between digits (2014/05/01, 5-1-2014,
+ * 2014-13-45), or a clock time (12:00).  Everything else is called NaN.
+ */
+DNG_HD bool dng_date_maybe_legacy(const uint8_t *p, int n)
 {
-	for (int i = 0; i < n; i++)
-		if (p[i] >= '0' && p[i] <= '9')
-			return false;
-	return true;
+	int seps = 0;
+	for (int i = 0; i + 2 < n; i++) {
+		const bool d0 = p[i] >= '0' && p[i] <= '9';
+		const bool d2 = p[i + 2] >= '0' && p[i + 2] <= '9';
+		if (d0 && d2 && (p[i + 1] == '-' || p[i + 1] == '/'))
+			seps++;
+		if (d0 && d2 && p[i + 1] == ':')
+			return true;
+	}
+	if (seps >= 2)
+		return true;
+	for (int i = 0; i + 2 < n; i++) {
+		const uint32_t a = p[i] | 0x20, b = p[i + 1] | 0x20,
+		    c = p[i + 2] | 0x20;
+		if (i > 0 && (uint32_t)((p[i - 1] | 0x20) - 'a') < 26u)
+			continue;		/* not the start of a word */
+		const uint32_t w = a << 16 | b << 8 | c;
+		if (w == 0x6a616e || w == 0x666562 || w == 0x6d6172 ||
+		    w == 0x617072 || w == 0x6d6179 || w == 0x6a756e ||
+		    w == 0x6a756c || w == 0x617567 || w == 0x736570 ||
+		    w == 0x6f6374 || w == 0x6e6f76 || w == 0x646563)
+			return true;
+	}
+	return false;
 }
 
 } /* namespace dng */

@@ -1136,7 +1136,7 @@ DNG_HD int process_metric(const u8 *rec, const DevPlan &P, u32 mi, RecState &R,
 				    (int)val_len(v.pk), &ms);
 				/* (not ISO, but V8's legacy parser might know it:
 				 * not ours to call NaN, jsdate.cuh) */
-				if (!ok && !dng_date_hopeless(rec + val_off(v.pk),
+				if (!ok && dng_date_maybe_legacy(rec + val_off(v.pk),
 				    (int)val_len(v.pk)))
 					ovf = 1;
 			} else if (t == T_STR || t == T_ARR) {
@@ -1144,7 +1144,8 @@ DNG_HD int process_metric(const u8 *rec, const DevPlan &P, u32 mi, RecState &R,
 				value_to_string(rec, v, kbuf, o, KEY_MAX, ovf,
 				    slow);
 				ok = dng_date_parse(kbuf, (int)o, &ms);
-				if (!ok && !dng_date_hopeless(kbuf, (int)o))
+				if (!ok && t == T_STR &&
+				    dng_date_maybe_legacy(kbuf, (int)o))
 					ovf = 1;
 			}
 			if (!ok) {

@@ -352,6 +352,25 @@ class Unsupported(Exception):
     """Input whose reference behaviour this restatement does not cover."""
 
 
+_MONTHS = (b'jan', b'feb', b'mar', b'apr', b'may', b'jun', b'jul', b'aug',
+           b'sep', b'oct', b'nov', b'dec')
+
+
+def date_maybe_legacy(b):
+    """Does this (non-ISO) string look like one of the forms V8's legacy
+    Date.parse exists for: a month name, two date separators between digits,
+    a clock time?  Those are not restated, so they are not called NaN either
+    (dragnet_b200/csrc/jsdate.cuh dng_date_maybe_legacy)."""
+    if len(re.findall(rb'(?=[0-9][-/][0-9])', b)) >= 2:
+        return True
+    if re.search(rb'[0-9]:[0-9]', b):
+        return True
+    for m in re.finditer(rb'[A-Za-z]+', b):
+        if m.group(0)[:3].lower() in _MONTHS and len(m.group(0)) >= 3:
+            return True
+    return False
+
+
 def date_parse_ms(b):
     m = _ISO.match(b)
     if not m:
@@ -525,7 +544,8 @@ def scan(plan, chunks):
                 else:
                     text = js_to_string(val)
                     ms = date_parse_ms(text)
-                    if ms is None and any(48 <= c <= 57 for c in text):
+                    if ms is None and isinstance(val, (bytes, str)) and \
+                            date_maybe_legacy(text):
                         # not in the ES5 format, but V8's legacy parser may
                         # well make a date of it: not restated, so not ours
                         # to call NaN (the CUDA path refuses such input too)

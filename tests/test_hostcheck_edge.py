@@ -103,13 +103,15 @@ def test_legacy_date_strings_are_refused_not_dropped(tmp_path):
     """A date string outside the ES5 format that V8's legacy Date.parse might
     accept is neither parsed nor called NaN: the device code flags the record
     unsupported (the scan then fails with DNG_EUNSUPPORTED) and the oracle
-    raises; a string without any digit is NaN (`baddate`) in both."""
+    raises; anything that does not even look like such a form is NaN
+    (`baddate`) in both."""
     import json
     import subprocess
     import dn_oracle
     from engines import build_hostcheck
     lines = [b'{"time":"2014-05-01T00:00:00Z","a":1}',
-             b'{"time":"nonsense","a":1}']
+             b'{"time":"nonsense","a":1}', b'{"time":" 12 ,x"}',
+             b'{"time":"gurble 7"}']
     plan = corpus.make_plan(
         ['-b', 'ts[date,field=time,aggr=lquantize,step=86400]'])
     p = tmp_path / 'ok.log'

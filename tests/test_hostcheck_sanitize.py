@@ -21,11 +21,14 @@ HC = os.path.join(ROOT, 'tests', 'hostcheck')
 @pytest.fixture(scope='module')
 def asan_exe(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp('asan') / 'hostcheck_asan')
+    subprocess.check_call(['make', '-s', '-C', CSRC, 'build/jit_blob.o'])
     subprocess.check_call(
         ['g++', '-std=c++17', '-O1', '-g', '-fsanitize=address,undefined',
-         '-fno-omit-frame-pointer', '-o', exe,
+         '-fno-omit-frame-pointer', '-I/usr/local/cuda/include', '-o', exe,
          os.path.join(HC, 'hostcheck.cpp'), os.path.join(CSRC, 'plan.cpp'),
-         os.path.join(CSRC, 'result.cpp'), os.path.join(CSRC, 'tmpl.cpp')])
+         os.path.join(CSRC, 'result.cpp'), os.path.join(CSRC, 'tmpl.cpp'),
+         os.path.join(CSRC, 'fast.cpp'), os.path.join(CSRC, 'jit.cpp'),
+         os.path.join(CSRC, 'build', 'jit_blob.o'), '-ldl'])
     return exe
 
 
@@ -42,8 +45,9 @@ def test_no_memory_errors_or_ub(asan_exe, tmp_path):
             ('scalars', corpus.EDGE_QUERIES[:6]),
             ('fuzz', corpus.EDGE_QUERIES[:30:4]),
             ('random', corpus.EDGE_QUERIES[:30:6])]
+    # (+ the F path: fast.cuh's matcher, stages and piece-wise key functions)
     env = dict(os.environ, DNG_HOSTCHECK_TMPL='1', DNG_HOSTCHECK_FAST='1',
-               ASAN_OPTIONS='detect_leaks=0')
+               DNG_HOSTCHECK_F='1', ASAN_OPTIONS='detect_leaks=0')
     n = 0
     for name, queries in jobs:
         path = tmp_path / (name + '.log')
