@@ -299,8 +299,9 @@ int learn_ftemplates(dng_scan *s, const std::vector<TCandidate> &cands,
 	}
 	s->jit.reset();
 	if (s->jit_mode && !blob.empty())
-		s->jit = jit_request(jit_source(blob.data(), blob.size()),
-		    s->device, (int)s->f_smem_max, s->jit_mode == 2);
+		s->jit = jit_request(jit_source(blob.data(), blob.size(), &s->fplan),
+		    (int)s->f_nsl, s->device, (int)s->f_smem_max,
+		    s->jit_mode == 2);
 	if (s->kernel_pref == 0)
 		s->f_kernel = s->warp_kernel && !blob.empty() &&
 		    covered * 10 >= sampled_lines * 9 &&
@@ -533,26 +534,22 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 	/* the matcher compiled for these templates, once it is there */
 	const bool jit = s->jit && s->jit->state.load() == 1 && s->ftmpl_bytes;
 	size_t smem = 0;
-	int ki = 3;
 	switch (nsl) {
 	case 7:
 		fkernel_slots<7>(s, a.nrows, &a.s1slots, &a.sslots);
 		smem = fkernel_smem<7>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
-		ki = 0;
 		if (!jit)
 			launch_fkernel<7>(s, a, grid);
 		break;
 	case 9:
 		fkernel_slots<9>(s, a.nrows, &a.s1slots, &a.sslots);
 		smem = fkernel_smem<9>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
-		ki = 1;
 		if (!jit)
 			launch_fkernel<9>(s, a, grid);
 		break;
 	case 11:
 		fkernel_slots<11>(s, a.nrows, &a.s1slots, &a.sslots);
 		smem = fkernel_smem<11>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
-		ki = 2;
 		if (!jit)
 			launch_fkernel<11>(s, a, grid);
 		break;
@@ -566,7 +563,7 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 	cudaError_t le = cudaSuccess;
 	if (jit) {
 		void *args[] = { &a };
-		le = cudaLaunchKernel((const void *)s->jit->kern[ki], dim3(grid),
+		le = cudaLaunchKernel((const void *)s->jit->kern, dim3(grid),
 		    dim3(DNG_NT), args, smem, s->stream);
 		s->jit_launches++;
 	}

@@ -155,6 +155,31 @@ struct FKeySmem {
 	}
 };
 
+#ifdef DNG_JIT_HOT
+/*
+ * The link-time-optimised build of the kernel (fast_jit.cu) keeps its rare,
+ * large paths out of the optimiser's way: they are compiled ahead of time
+ * (fast_jit_cold.cu) and only linked in.
+ */
+extern "C" __device__ void dng_cold_slow_add(FSmem m, const FPlan *F,
+    u32 defmask, u32 klen, STab stab, const GTable *gt);
+extern "C" __device__ void dng_cold_miss(const u8 *data,
+    unsigned long long start, unsigned long long beg, unsigned long long end,
+    const DevPlan *plan, STab stab, const GTable *gt,
+    unsigned long long *counters);
+extern "C" __device__ void dng_cold_flush(STab stab, u32 s1slots, u32 sslots,
+    const GTable *tab);
+/*
+ * The scan's plan as a CONSTANT of the generated code (jit.cpp writes it out
+ * with its initialiser): after link-time optimisation the stage and key code
+ * below is specialised to it -- column loops unrolled, kinds and entry points
+ * folded, absent filters gone.  (The copy in shared memory is still what the
+ * rare paths are handed.)
+ */
+extern "C" __constant__ const FPlan dng_jplan;
+#define fslow_add dng_cold_slow_add
+#define fmiss_inline dng_cold_miss
+#else
 /* first sighting of a key in this CTA, or a key the inline tier has no room
  * for: materialise it and take the general tally path */
 __device__ __noinline__ void fslow_add(FSmem m, const FPlan *F, u32 defmask,
@@ -165,6 +190,8 @@ __device__ __noinline__ void fslow_add(FSmem m, const FPlan *F, u32 defmask,
 	const unsigned long long *kw = (const unsigned long long *)kbuf;
 	shared_add(stab, *gt, key_hash_words(kw, klen), kw, klen, 1);
 }
+
+#endif /* DNG_JIT_HOT */
 
 __device__ __forceinline__ unsigned long long lds64_acquire(u32 addr)
 {
@@ -186,8 +213,9 @@ __device__ __forceinline__ void sts64_release(u32 addr, unsigned long long v)
  * read with acquire semantics (plain shared loads and stores in SASS: no
  * fence on the path every record takes).
  */
-__device__ __forceinline__ void ftally(FSmem &m, const FPlan &F, u32 defmask,
-    u32 h, u32 klen, const STab &stab, const GTable &gt)
+__device__ __forceinline__ void ftally(FSmem &m, const FPlan &F,
+    const FPlan *Fcold, u32 defmask, u32 h, u32 klen, const STab &stab,
+    const GTable &gt)
 {
 	if (klen <= DNG_SKEY) {
 		const unsigned long long claim = (unsigned long long)(h | 1u);
@@ -223,9 +251,10 @@ __device__ __forceinline__ void ftally(FSmem &m, const FPlan &F, u32 defmask,
 			idx = (idx + 1) & stab.mask1;
 		}
 	}
-	fslow_add(m, &F, defmask, klen, stab, &gt);
+	fslow_add(m, Fcold, defmask, klen, stab, &gt);
 }
 
+#ifndef DNG_JIT_HOT
 /*
  * A record the miss list had no room for: the general parser, from HBM, right
  * here.  Entirely out of line, with its own counters (added to the global
@@ -264,6 +293,8 @@ __device__ __noinline__ void fmiss_inline(const u8 *data,
 			atomicAdd(&counters[k], (unsigned long long)vals[k]);
 }
 
+#endif /* DNG_JIT_HOT */
+
 /* append to the miss list, or parse here when it is full */
 __device__ __forceinline__ void fmiss_put(const FScanArgs &a, const STab &stab,
     u32 at, unsigned long long beg, unsigned long long end)
@@ -295,7 +326,11 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 	typedef FWarpSmem<NSL> WS;
 	constexpr u32 CHUNK = WS::CHUNK, SLICE = 16 * NSL, D0 = DNG_F_PRE;
 	extern __shared__ __align__(128) u8 smem[];
+#ifdef DNG_JIT_HOT
+	const FPlan &F = dng_jplan;
+#else
 	const FPlan &F = *(const FPlan *)smem;
+#endif
 	u8 *sp = smem + FPLAN_SMEM;
 	const u32 tmpl_sa = smem_u32(sp);
 	sp += a.tmpl_bytes;
@@ -589,8 +624,8 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 						if (fo == FO_AGGR) {
 							if (slow)
 								atomicAdd(&s_drop[1], 1u);
-							ftally(m, F, defmask, h, klen, stab,
-							    a.tab);
+							ftally(m, F, (const FPlan *)smem, defmask,
+							    h, klen, stab, a.tab);
 						}
 					}
 					const bool done = fo != FO_MISS;
@@ -646,7 +681,12 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 		}
 	}
 
+#ifdef DNG_JIT_HOT
+	__syncthreads();
+	dng_cold_flush(stab, a.s1slots, a.sslots, &a.tab);
+#else
 	flush_tally(stab, a.s1slots, a.sslots, a.tab);
+#endif
 	if (lane == 0) {
 		if (ntmpl) {
 			atomicAdd(&a.counters[CTR_LINES], (unsigned long long)ntmpl);
@@ -671,13 +711,16 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 	}
 }
 
+#ifndef DNG_JIT_HOT
 template <int NSL>
 __global__ void __launch_bounds__(DNG_NT, 1)
 scan_kernel_f(const FScanArgs a)
 {
 	fscan_body<NSL, false>(a);
 }
+#endif
 
+#ifndef DNG_JIT_HOT
 /* ---- the records the F path did not take ------------------------------------ */
 
 struct FMissArgs {
@@ -749,6 +792,8 @@ scan_miss_kernel(const FMissArgs a)
 	flush_tally(stab, a.s1slots, a.sslots, a.tab);
 	flush_counters(a.counters, C, nlong, 0);
 }
+
+#endif /* DNG_JIT_HOT */
 
 } /* namespace dng */
 #endif

@@ -15,12 +15,16 @@
 #include <vector>
 
 #include "jit.h"
+#include "fast.h"
 #include "tmpl.h"
 
-/* the relocatable build of the kernel (fast_jit.cu) and fscan.cuh as text:
- * build/jit_blob.S */
-extern "C" const unsigned char dng_fast_jit_cubin[];
-extern "C" const unsigned char dng_fast_jit_cubin_end[];
+/* jit_blob.S: the LTO-IR builds of the kernel (fast_jit.cu), its rare paths as
+ * SASS (fast_jit_cold.cu) and fscan.cuh as text */
+#define BLOB(n) extern "C" const unsigned char n[]; \
+	extern "C" const unsigned char n##_end[];
+BLOB(dng_jit_hot7) BLOB(dng_jit_hot9) BLOB(dng_jit_hot11) BLOB(dng_jit_hot13)
+BLOB(dng_jit_cold)
+#undef BLOB
 extern "C" const char dng_fscan_src[];
 extern "C" const char dng_fscan_src_end[];
 
@@ -157,11 +161,70 @@ void successors(const JN &n, std::vector<int> &out)
 
 } /* namespace */
 
-std::string jit_source(const u8 *blob, size_t bytes, const char *prelude)
+/*
+ * The plan, written out as the constant the LTO build of the kernel refers to
+ * (fast_kernel.cuh dng_jplan): the same bytes as the FPlan the scan uploads,
+ * field by field, under struct declarations that are checked against the
+ * library's by size.
+ */
+static void plan_source(const FPlan &F, std::string &s)
+{
+	s += "struct Src { u8 kind; u8 idx; };\n"
+	    "/* (binary64 fields as their bit patterns: NaN and infinity have no\n"
+	    " * literal; same layout as the double the kernel reads) */\n"
+	    "struct Leaf { u64 cnum; unsigned short coff, clen; short jt, jf; "
+	    "u8 op; u8 cstr; Src src; u32 pad; };\n"
+	    "struct Col { u64 step; Src src; u8 kind; u8 pad[5]; };\n"
+	    "struct alignas(16) FPlan { Leaf code[16]; Col col[6]; "
+	    "u8 syn_path[2]; short ds_entry, user_entry, time_entry; "
+	    "u8 nsyn, ncols, npaths, ok; u8 ord_row[6]; u8 nrows; u8 pad[5]; "
+	    "char pool[512]; };\n";
+	appendf(s, "static_assert(sizeof (Leaf) == %zu && sizeof (Col) == %zu && "
+	    "sizeof (FPlan) == %zu, \"plan layout\");\n", sizeof (Leaf),
+	    sizeof (Col), sizeof (FPlan));
+	static_assert(F_MAXCODE == 16 && F_MAXCOLS == 6 && F_MAXSYN == 2 &&
+	    F_POOL == 512, "plan_source() spells these out");
+	s += "extern \"C\" __constant__ const FPlan dng_jplan = {\n	{\n";
+	for (int i = 0; i < F_MAXCODE; i++) {
+		const Leaf &l = F.code[i];
+		u64 cb;
+		memcpy(&cb, &l.cnum, 8);
+		appendf(s, "		{ 0x%016llxull, %u, %u, %d, %d, %u, %u, { %u, %u }, 0 },\n",
+		    (unsigned long long)cb, (unsigned)l.coff, (unsigned)l.clen, (int)l.jt,
+		    (int)l.jf, (unsigned)l.op, (unsigned)l.cstr,
+		    (unsigned)l.src.kind, (unsigned)l.src.idx);
+	}
+	s += "	},\n	{\n";
+	for (int i = 0; i < F_MAXCOLS; i++) {
+		const Col &c = F.col[i];
+		u64 sb;
+		memcpy(&sb, &c.step, 8);
+		appendf(s, "		{ 0x%016llxull, { %u, %u }, %u, { 0, 0, 0, 0, 0 } },\n",
+		    (unsigned long long)sb, (unsigned)c.src.kind, (unsigned)c.src.idx,
+		    (unsigned)c.kind);
+	}
+	appendf(s, "	},\n	{ %u, %u }, %d, %d, %d, %u, %u, %u, %u,\n",
+	    (unsigned)F.syn_path[0], (unsigned)F.syn_path[1], (int)F.ds_entry,
+	    (int)F.user_entry, (int)F.time_entry, (unsigned)F.nsyn,
+	    (unsigned)F.ncols, (unsigned)F.npaths, (unsigned)F.ok);
+	appendf(s, "	{ %u, %u, %u, %u, %u, %u }, %u, { 0, 0, 0, 0, 0 },\n	{ ",
+	    (unsigned)F.ord_row[0], (unsigned)F.ord_row[1],
+	    (unsigned)F.ord_row[2], (unsigned)F.ord_row[3],
+	    (unsigned)F.ord_row[4], (unsigned)F.ord_row[5], (unsigned)F.nrows);
+	for (int i = 0; i < F_POOL; i++)
+		appendf(s, "%d,%s", (int)(signed char)F.pool[i],
+		    i % 32 == 31 ? "\n	  " : "");
+	s += " }\n};\n";
+}
+
+std::string jit_source(const u8 *blob, size_t bytes, const FPlan *plan,
+    const char *prelude)
 {
 	std::string s;
 	s += "/* generated by libdragnet_gpu (jit.cpp) */\n";
 	s += prelude ? prelude : PRELUDE;
+	if (plan)
+		plan_source(*plan, s);
 	s.append(dng_fscan_src, (size_t)(dng_fscan_src_end - dng_fscan_src));
 	s += "\nextern \"C\" __device__ unsigned dng_jmatch(unsigned ra, "
 	    "unsigned len, unsigned active, unsigned caps)\n{\n"
@@ -396,8 +459,8 @@ struct Libs {
 	int (*CreateProgram)(nvrtcProgram *, const char *, const char *, int,
 	    const char *const *, const char *const *) = nullptr;
 	int (*CompileProgram)(nvrtcProgram, int, const char *const *) = nullptr;
-	int (*GetCUBINSize)(nvrtcProgram, size_t *) = nullptr;
-	int (*GetCUBIN)(nvrtcProgram, char *) = nullptr;
+	int (*GetLTOIRSize)(nvrtcProgram, size_t *) = nullptr;
+	int (*GetLTOIR)(nvrtcProgram, char *) = nullptr;
 	int (*GetProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
 	int (*GetProgramLog)(nvrtcProgram, char *) = nullptr;
 	int (*DestroyProgram)(nvrtcProgram *) = nullptr;
@@ -460,8 +523,8 @@ Libs &libs()
 	if (!L.field) { L.err = "missing " name; return; }
 		RTC(CreateProgram, "nvrtcCreateProgram")
 		RTC(CompileProgram, "nvrtcCompileProgram")
-		RTC(GetCUBINSize, "nvrtcGetCUBINSize")
-		RTC(GetCUBIN, "nvrtcGetCUBIN")
+		RTC(GetLTOIRSize, "nvrtcGetLTOIRSize")
+		RTC(GetLTOIR, "nvrtcGetLTOIR")
 		RTC(GetProgramLogSize, "nvrtcGetProgramLogSize")
 		RTC(GetProgramLog, "nvrtcGetProgramLog")
 		RTC(DestroyProgram, "nvrtcDestroyProgram")
@@ -491,12 +554,22 @@ double now_ms()
 
 } /* namespace */
 
-bool jit_build(const std::string &source, std::string &cubin, std::string &err,
-    double *compile_ms, double *link_ms)
+bool jit_build(const std::string &source, int nsl, std::string &cubin,
+    std::string &err, double *compile_ms, double *link_ms)
 {
 	Libs &L = libs();
 	if (!L.ok) {
 		err = L.err;
+		return false;
+	}
+	const unsigned char *hot, *hot_end;
+	switch (nsl) {
+	case 7: hot = dng_jit_hot7; hot_end = dng_jit_hot7_end; break;
+	case 9: hot = dng_jit_hot9; hot_end = dng_jit_hot9_end; break;
+	case 11: hot = dng_jit_hot11; hot_end = dng_jit_hot11_end; break;
+	case 13: hot = dng_jit_hot13; hot_end = dng_jit_hot13_end; break;
+	default:
+		err = "no kernel for this slice size";
 		return false;
 	}
 	const double t0 = now_ms();
@@ -506,11 +579,11 @@ bool jit_build(const std::string &source, std::string &cubin, std::string &err,
 		err = "nvrtcCreateProgram failed";
 		return false;
 	}
-	/* relocatable, and within the register budget of the kernel it is
-	 * linked into (__launch_bounds__(768, 1)) */
-	const char *opts[] = { "-arch=sm_100a", "-rdc=true", "-maxrregcount=80",
-	    "-std=c++17", "-lineinfo" };
-	const int rc = L.CompileProgram(prog, 5, opts);
+	/* LTO-IR, within the register budget of the kernel it becomes part of
+	 * (__launch_bounds__(768, 1)) */
+	const char *opts[] = { "-arch=sm_100a", "-rdc=true", "-dlto",
+	    "-maxrregcount=80", "-std=c++17", "-lineinfo" };
+	const int rc = L.CompileProgram(prog, 6, opts);
 	if (rc != 0) {
 		size_t n = 0;
 		L.GetProgramLogSize(prog, &n);
@@ -522,26 +595,29 @@ bool jit_build(const std::string &source, std::string &cubin, std::string &err,
 		return false;
 	}
 	size_t n = 0;
-	L.GetCUBINSize(prog, &n);
-	std::string obj(n, '\0');
-	L.GetCUBIN(prog, &obj[0]);
+	L.GetLTOIRSize(prog, &n);
+	std::string ir(n, '\0');
+	L.GetLTOIR(prog, &ir[0]);
 	L.DestroyProgram(&prog);
 	const double t1 = now_ms();
 	if (compile_ms)
 		*compile_ms = t1 - t0;
 
 	nvJitLinkHandle h = nullptr;
-	const char *lopts[] = { "-arch=sm_100a" };
-	if (L.LCreate(&h, 1, lopts) != 0) {
+	const char *lopts[] = { "-arch=sm_100a", "-lto", "-maxrregcount=80",
+	    "-lineinfo" };
+	if (L.LCreate(&h, 4, lopts) != 0) {
 		err = "nvJitLinkCreate failed";
 		return false;
 	}
-	const int NVJITLINK_INPUT_CUBIN = 1;
-	int lrc = L.LAddData(h, NVJITLINK_INPUT_CUBIN, dng_fast_jit_cubin,
-	    (size_t)(dng_fast_jit_cubin_end - dng_fast_jit_cubin), "fast_jit");
+	const int IN_CUBIN = 1, IN_LTOIR = 3, IN_FATBIN = 4;
+	int lrc = L.LAddData(h, IN_FATBIN, hot, (size_t)(hot_end - hot),
+	    "fast_jit");
 	if (lrc == 0)
-		lrc = L.LAddData(h, NVJITLINK_INPUT_CUBIN, obj.data(), obj.size(),
-		    "dng_jmatch");
+		lrc = L.LAddData(h, IN_LTOIR, ir.data(), ir.size(), "dng_jmatch");
+	if (lrc == 0)
+		lrc = L.LAddData(h, IN_CUBIN, dng_jit_cold,
+		    (size_t)(dng_jit_cold_end - dng_jit_cold), "fast_jit_cold");
 	if (lrc == 0)
 		lrc = L.LComplete(h);
 	if (lrc != 0) {

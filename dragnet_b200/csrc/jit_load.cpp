@@ -29,25 +29,20 @@ struct Workers {
 	}
 } g_workers;
 
-void build_into(std::shared_ptr<JitKernels> k, std::string source, int dev,
-    int smem_max)
+void build_into(std::shared_ptr<JitKernels> k, std::string source, int nsl,
+    int dev, int smem_max)
 {
 	std::string cubin, err;
-	bool ok = jit_build(source, cubin, err, &k->compile_ms, &k->link_ms);
+	bool ok = jit_build(source, nsl, cubin, err, &k->compile_ms, &k->link_ms);
 	if (ok) {
 		cudaSetDevice(dev);
 		cudaError_t e = cudaLibraryLoadData(&k->lib, cubin.data(), nullptr,
 		    nullptr, 0, nullptr, nullptr, 0);
-		static const char *names[4] = { "dng_scan_kernel_j7",
-		    "dng_scan_kernel_j9", "dng_scan_kernel_j11",
-		    "dng_scan_kernel_j13" };
-		for (int i = 0; i < 4 && e == cudaSuccess; i++) {
-			e = cudaLibraryGetKernel(&k->kern[i], k->lib, names[i]);
-			if (e == cudaSuccess)
-				e = cudaFuncSetAttribute((const void *)k->kern[i],
-				    cudaFuncAttributeMaxDynamicSharedMemorySize,
-				    smem_max);
-		}
+		if (e == cudaSuccess)
+			e = cudaLibraryGetKernel(&k->kern, k->lib, "dng_scan_kernel_j");
+		if (e == cudaSuccess)
+			e = cudaFuncSetAttribute((const void *)k->kern,
+			    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
 		if (e != cudaSuccess) {
 			ok = false;
 			err = std::string("loading the linked kernel: ") +
@@ -65,13 +60,14 @@ void build_into(std::shared_ptr<JitKernels> k, std::string source, int dev,
 
 } /* namespace */
 
-std::shared_ptr<JitKernels> jit_request(const std::string &source, int dev,
-    int smem_max, bool wait)
+std::shared_ptr<JitKernels> jit_request(const std::string &source, int nsl,
+    int dev, int smem_max, bool wait)
 {
 	u64 hsh = 1469598103934665603ull;
 	for (unsigned char c : source)
 		hsh = (hsh ^ c) * 1099511628211ull;
 	hsh ^= (u64)source.size() << 40;
+	hsh = (hsh ^ (u64)nsl) * 1099511628211ull;
 	std::unique_lock<std::mutex> g(g_mu);
 	std::shared_ptr<JitKernels> k;
 	auto it = g_cache.find(std::make_pair(dev, hsh));
@@ -83,10 +79,10 @@ std::shared_ptr<JitKernels> jit_request(const std::string &source, int dev,
 		g_cache[std::make_pair(dev, hsh)] = k;
 		if (wait) {
 			g.unlock();
-			build_into(k, source, dev, smem_max);
+			build_into(k, source, nsl, dev, smem_max);
 			g.lock();
 		} else {
-			g_workers.th.emplace_back(build_into, k, source, dev,
+			g_workers.th.emplace_back(build_into, k, source, nsl, dev,
 			    smem_max);
 		}
 	}

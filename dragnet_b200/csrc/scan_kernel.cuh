@@ -494,6 +494,7 @@ __device__ __forceinline__ u32 byte_range_mask(u32 p, u32 lo, u32 hi)
 	return m;
 }
 
+#ifndef DNG_JIT_HOT	/* (the LTO build of the F kernel: none of the general path) */
 /* ---- one record ----------------------------------------------------------- */
 
 /*
@@ -714,6 +715,8 @@ __device__ __forceinline__ bool scan_record(WinCtx &w, u32 phase, bool have,
 	return failed;
 }
 
+#endif /* DNG_JIT_HOT */
+
 /* end of a kernel, part 1: the CTA's tally cache -> the global table */
 __device__ __forceinline__ void flush_tally(const STab &stab, u32 s1slots,
     u32 sslots, const GTable &tab)
@@ -770,6 +773,7 @@ __device__ __forceinline__ void flush_counters(unsigned long long *counters,
 	}
 }
 
+#ifndef DNG_JIT_HOT
 /* end of a kernel: shared tally cache -> global table, counters -> global */
 __device__ __forceinline__ void scan_epilogue(const ScanArgs &a,
     const DevPlan &P, const STab &stab, const LocalCounters &C,
@@ -819,6 +823,8 @@ __device__ __noinline__ u32 slice_newlines(u32 sbase, u32 c0, u32 c1, u32 lower)
 	}
 	return cnt | (hot << 16);
 }
+
+#endif /* DNG_JIT_HOT */
 
 #ifndef DNG_NO_GENERAL_KERNELS	/* (fast_jit.cu only wants the shared parts) */
 /* ---- the kernel ------------------------------------------------------------ */
@@ -1379,8 +1385,6 @@ scan_kernel_w(const ScanArgs a)
 	scan_epilogue(a, P, stab, C, s_mctr, nlong, ntmpl);
 }
 
-#endif /* DNG_NO_GENERAL_KERNELS */
-
 /* gather occupied entries: out[i] = {koff-1, klen, count} */
 struct OutEntry {
 	unsigned long long count;
@@ -1414,6 +1418,8 @@ __global__ void find_nl_kernel(const u8 *data, unsigned long long lo,
 		}
 	}
 }
+
+#endif /* DNG_NO_GENERAL_KERNELS */
 
 } /* namespace dng */
 #endif

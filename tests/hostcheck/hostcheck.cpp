@@ -70,14 +70,15 @@ static const char *HOST_PRELUDE =
 
 typedef unsigned (*jmatch_fn)(unsigned, unsigned, unsigned, unsigned);
 
-static jmatch_fn host_jit(const std::vector<u8> &fblob, unsigned char ***mem)
+static jmatch_fn host_jit(const std::vector<u8> &fblob, const FPlan *fplan,
+    unsigned char ***mem)
 {
-	std::string dev = jit_source(fblob.data(), fblob.size());
+	std::string dev = jit_source(fblob.data(), fblob.size(), fplan);
 	std::string cubin, err;
 	double cms = 0, lms = 0;
 	/* DNG_HOSTCHECK_JIT=2: the device build too (a second or two) */
 	if (atoi(getenv("DNG_HOSTCHECK_JIT")) >= 2) {
-		if (!jit_build(dev, cubin, err, &cms, &lms)) {
+		if (!jit_build(dev, 13, cubin, err, &cms, &lms)) {
 			fprintf(stderr, "jit_build: %s\n", err.c_str());
 			exit(4);
 		}
@@ -93,7 +94,8 @@ static jmatch_fn host_jit(const std::vector<u8> &fblob, unsigned char ***mem)
 		fwrite(cubin.data(), 1, cubin.size(), d2);
 		fclose(d2);
 	}
-	std::string host = jit_source(fblob.data(), fblob.size(), HOST_PRELUDE);
+	std::string host = jit_source(fblob.data(), fblob.size(), nullptr,
+	    HOST_PRELUDE);
 	char dir[] = "/tmp/dng_jit_XXXXXX";
 	if (!mkdtemp(dir))
 		exit(4);
@@ -202,7 +204,7 @@ int main(int argc, char **argv)
 	unsigned char **jmem = nullptr;
 	static unsigned char jbuf[65536];
 	if (getenv("DNG_HOSTCHECK_JIT") != nullptr && !fblob.empty()) {
-		jm = host_jit(fblob, &jmem);
+		jm = host_jit(fblob, &FP, &jmem);
 		*jmem = jbuf;
 	}
 	static LocalCounters MCs[MAX_METRICS];
