@@ -528,7 +528,10 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 	 * every warp of the grid busy */
 	const u32 nwarps = grid * DNG_NW;
 	a.seg = std::max<u32>(1, std::min<u32>(DNG_F_SEG,
-	    a.nchunks / (nwarps * 4)));
+	    a.nchunks / (nwarps * 8)));
+	/* the segment queue: [1] of the miss counter's allocation */
+	a.seg_next = s->d_miss_n + 1;
+	cudaMemsetAsync(s->d_miss_n, 0, 2 * sizeof (u32), s->stream);
 	cudaEvent_t e0 = get_event(s), e1 = get_event(s);
 	cudaEventRecord(e0, s->stream);
 	/* the matcher compiled for these templates, once it is there */
@@ -587,7 +590,6 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 		    s->stream>>>(ma);
 		le = cudaGetLastError();
 	}
-	cudaMemsetAsync(s->d_miss_n, 0, sizeof (u32), s->stream);
 	cudaEventRecord(e1, s->stream);
 	if (!s->h_live && HOST_ALLOC(&s->h_live, 16 * sizeof (unsigned long long))
 	    == cudaSuccess)

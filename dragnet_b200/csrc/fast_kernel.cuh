@@ -41,7 +41,7 @@ namespace dng {
 #define DNG_F_SLACK 64
 #define DNG_F_NLCAP 128			/* newline positions per chunk */
 #define DNG_F_MAXLINE DNG_F_PRE		/* host: sampled lines must be shorter */
-#define DNG_F_SEG 32			/* chunks per segment (at most) */
+#define DNG_F_SEG 16			/* chunks per segment (at most) */
 
 struct MissEnt {
 	unsigned long long beg;		/* ~0: unknown, before `end` */
@@ -66,6 +66,7 @@ struct FScanArgs {
 	MissEnt *miss;
 	u32 miss_cap;
 	u32 *miss_n;
+	u32 *seg_next;			/* segment queue: zero at launch */
 };
 
 /* per-warp shared memory: buffer, newline positions, mbarrier */
@@ -85,6 +86,59 @@ static inline size_t fkernel_smem(u32 tmpl_bytes, u32 s1slots, u32 sslots,
 	return FPLAN_SMEM + tmpl_bytes + (size_t)s1slots * sizeof (SSlot1) +
 	    (size_t)sslots * sizeof (SSlot) + (size_t)nrows * DNG_NT * 4 +
 	    (size_t)DNG_NW * FWarpSmem<NSL>::BYTES;
+}
+
+/* mbarrier / TMA helpers on 32-bit shared addresses (no generic pointers to
+ * keep alive across the record loop) */
+__device__ __forceinline__ void mbar_init_sa(u32 bar, u32 count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
+	    :: "r"(bar), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx_sa(u32 bar, u32 bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+	    :: "r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_1d_sa(u32 dst, const void *src,
+    u32 bytes, u32 bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::"
+	    "complete_tx::bytes [%0], [%1], %2, [%3];"
+	    :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_sa(u32 bar, u32 parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}\n"
+	    :: "r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void sts8(u32 addr, u32 v)
+{
+	asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void sts16(u32 addr, u32 v)
+{
+	asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void sts128(u32 addr, uint4 v)
+{
+	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+	    :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ void sts32(u32 addr, u32 v)
@@ -346,10 +400,11 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 
 	const u32 tid = threadIdx.x;
 	const u32 lane = tid & 31, wid = tid >> 5;
-	u8 *sbuf = sp + wid * WS::BYTES;		/* this warp's buffer */
-	unsigned short *nlpos = (unsigned short *)(sbuf + WS::BUF);
-	u64 *mbar = (u64 *)(sbuf + WS::BUF + 2 * DNG_F_NLCAP);
-	const u32 sb = smem_u32(sbuf);
+	/* this warp's buffer, newline positions (u16) and mbarrier: shared
+	 * addresses */
+	const u32 sb = smem_u32(sp) + wid * WS::BYTES;
+	const u32 nlpos = sb + WS::BUF;
+	const u32 mbar = sb + WS::BUF + 2 * DNG_F_NLCAP;
 
 	{	/* plan, templates -> shared; clear the tally cache */
 		const uint4 *src = (const uint4 *)a.fplan;
@@ -367,7 +422,7 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 		for (u32 i = tid; i < tab_bytes / 16; i += DNG_NT)
 			tz[i] = z;
 		if (lane == 0)
-			mbar_init(mbar, 1);
+			mbar_init_sa(mbar, 1);
 	}
 	__syncthreads();
 
@@ -387,11 +442,18 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 	u32 ntmpl = 0, naggr = 0, parity = 0;
 	const u32 ltmask = (1u << lane) - 1;
 
+	/*
+	 * Segments are handed out through a counter: a warp that finishes
+	 * early takes the next one, so that the launch ends within a segment's
+	 * time of its last warp (static shares left 13% of the warp time parked
+	 * at the final barrier).  The first round is implicit -- warp gw takes
+	 * segment gw, spread over the SMs -- the counter hands out the rest.
+	 */
 	const u32 nwarps = gridDim.x * DNG_NW;
-	const u32 gw = wid * gridDim.x + blockIdx.x;	/* spread segments over SMs */
+	const u32 gw = wid * gridDim.x + blockIdx.x;
 	const u32 nseg = (a.nchunks + a.seg - 1) / a.seg;
 
-	for (u32 seg = gw; seg < nseg; seg += nwarps) {
+	for (u32 seg = gw; seg < nseg; ) {
 		const u32 ch0 = seg * a.seg;
 		const u32 ch1 = min(ch0 + a.seg, a.nchunks);
 		/* the open record: where it starts in the buffer (may be
@@ -412,7 +474,7 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 				const uint4 v = lds128(sb + D0 + CHUNK - DNG_F_PRE +
 				    16 * lane);
 				__syncwarp();
-				*(uint4 *)(sbuf + 16 * lane) = v;
+				sts128(sb + 16 * lane, v);
 				__syncwarp();
 			}
 			if (lane == 0) {
@@ -420,28 +482,25 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 				asm volatile("fence.proxy.async.shared::cta;"
 				    ::: "memory");
 				if (bulk + pre) {
-					mbar_expect_tx(mbar, bulk + pre);
+					mbar_expect_tx_sa(mbar, bulk + pre);
 					if (bulk)
-						tma_load_1d(sbuf + D0, a.data + g0,
+						tma_load_1d_sa(sb + D0, a.data + g0,
 						    bulk, mbar);
 					if (pre)
-						tma_load_1d(sbuf, a.data + g0 -
+						tma_load_1d_sa(sb, a.data + g0 -
 						    DNG_F_PRE, DNG_F_PRE, mbar);
 				}
 				/* start pulling this warp's next chunk into L2 */
-				unsigned long long nx = g0 + CHUNK;
-				if (ch + 1 == ch1)
-					nx = (unsigned long long)(seg + nwarps) *
-					    a.seg * CHUNK;
-				if (nx + CHUNK <= a.nbytes)
+				const unsigned long long nx = g0 + CHUNK;
+				if (ch + 1 < ch1 && nx + CHUNK <= a.nbytes)
 					asm volatile("cp.async.bulk.prefetch.L2."
 					    "global [%0], %1;" :: "l"(a.data + nx),
 					    "r"(CHUNK) : "memory");
 			}
 			for (u32 i = bulk + lane; i < dlen; i += 32)
-				sbuf[D0 + i] = a.data[g0 + i];
+				sts8(sb + D0 + i, a.data[g0 + i]);
 			if (bulk || (first && g0)) {
-				mbar_wait(mbar, parity);
+				mbar_wait_sa(mbar, parity);
 				parity ^= 1;
 			}
 			__syncwarp();
@@ -565,7 +624,7 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 					beg0 = last + 1;
 			} else if (total) {
 				if (cnt == 1 && one) {
-					nlpos[mybase] = (unsigned short)one;
+					sts16(nlpos + 2 * mybase, one);
 				} else if (cnt) {
 					u32 idx = mybase;
 #pragma unroll 1
@@ -579,8 +638,8 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 								const u32 pos = p + 4 * q +
 								    ((__ffs(mk) - 1) >> 3);
 								if (pos >= lo && pos < hi)
-									nlpos[idx++] =
-									    (unsigned short)pos;
+									sts16(nlpos + 2 * idx++,
+									    pos);
 							}
 						}
 					}
@@ -593,8 +652,9 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 					int beg = 0;
 					u32 end = 0;
 					if (have) {
-						end = nlpos[r];
-						beg = r ? (int)nlpos[r - 1] + 1 : beg0;
+						end = lds16(nlpos + 2 * r);
+						beg = r ? (int)lds16(nlpos + 2 * r - 2) + 1 :
+						    beg0;
 					}
 					/* (captures carry 12-bit offsets and lengths) */
 					const bool inbuf = have && beg >= 0 &&
@@ -664,7 +724,7 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 					}
 				}
 				__syncwarp();
-				const u32 lastnl = nlpos[total - 1];
+				const u32 lastnl = lds16(nlpos + 2 * (total - 1));
 				beg0 = (int)lastnl + 1;
 				open_abs = g0 - D0 + lastnl + 1;
 				__syncwarp();
@@ -679,6 +739,10 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 			if (beg0 < 0)
 				beg0 = -1;
 		}
+		/* the next segment nobody has taken yet */
+		if (lane == 0)
+			seg = nwarps + atomicAdd(a.seg_next, 1u);
+		seg = __shfl_sync(0xffffffffu, seg, 0);
 	}
 
 #ifdef DNG_JIT_HOT
