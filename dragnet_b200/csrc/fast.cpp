@@ -41,8 +41,14 @@ void fplan_build(const DevPlan &P, FPlan &F)
 		} else {
 			lf.coff = lf.clen = 0;
 		}
+		/* (plan.cpp only ever patches a jump to a later leaf; the
+		 * unrolled evaluator of the link-time optimised build relies
+		 * on it) */
+		if ((lf.jt >= 0 && lf.jt <= (int)i) || (lf.jf >= 0 && lf.jf <= (int)i))
+			return;
 		F.code[i] = lf;
 	}
+	F.ncode = P.ncode;
 	for (u32 j = 0; j < M.nsyn; j++) {
 		const Src s = P.syn[j];
 		if (s.kind == SRC_PATH && s.idx < P.npaths)

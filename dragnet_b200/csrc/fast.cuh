@@ -22,6 +22,19 @@
 #include "fast.h"
 #include "tmpl.cuh"
 
+/*
+ * Loops over the plan (its three filters, its synthetic fields, its columns):
+ * rolled up in the ahead-of-time build, where the plan is data and unrolling
+ * only multiplies the interpretive code; fully unrolled in the link-time
+ * optimised build (fast_jit.cu), where the plan is a constant and every
+ * iteration folds to the few instructions its column or filter needs.
+ */
+#ifdef DNG_JIT_HOT
+#define DNG_PLAN_LOOP _Pragma("unroll")
+#else
+#define DNG_PLAN_LOOP _Pragma("unroll 1")
+#endif
+
 namespace dng {
 
 #include "fscan.cuh"		/* (includes nothing: lives in this namespace) */
@@ -228,6 +241,22 @@ DNG_HD int feval(M &m, const FPlan &F, int entry, u32 defmask, double s0,
     double s1, bool &miss)
 {
 	int pc = entry;
+#ifdef DNG_JIT_HOT
+	/* the plan is a constant here: one block per leaf, in order (jumps
+	 * only go forward), each folded down to its own comparison */
+#pragma unroll
+	for (int i = 0; i < F_MAXCODE; i++) {
+		if (i >= (int)F.ncode || pc != i)
+			continue;
+		const Leaf &lf = F.code[i];
+		const int r = feval_leaf(m, F, lf, defmask, s0, s1, miss);
+		if (miss)
+			return 0;
+		if (r < 0)
+			return -1;
+		pc = r ? lf.jt : lf.jf;
+	}
+#else
 	while (pc >= 0) {
 		const Leaf &lf = F.code[pc];
 		const int r = feval_leaf(m, F, lf, defmask, s0, s1, miss);
@@ -237,6 +266,7 @@ DNG_HD int feval(M &m, const FPlan &F, int entry, u32 defmask, double s0,
 			return -1;
 		pc = r ? lf.jt : lf.jf;
 	}
+#endif
 	return pc == -1;
 }
 
@@ -300,13 +330,13 @@ DNG_HD u32 fstage(M &m, const FPlan &F, u32 defmask, double &s0, double &s1)
 	s0 = s1 = 0;
 	/* datasource filter, user filter, [dates,] time filter: one copy of
 	 * the evaluator for the three */
-#pragma unroll 1
+DNG_PLAN_LOOP
 	for (u32 k = 0; k < 3; k++) {
 		if (k == 2 && F.nsyn) {
 			/* lib/stream-synthetic.js:37-85: only the first error
 			 * of a record is counted, but every field is looked at */
 			u32 err = 0;
-#pragma unroll 1
+DNG_PLAN_LOOP
 			for (u32 j = 0; j < F.nsyn; j++) {
 				const u32 pi = F.syn_path[j];
 				double v = 0;
@@ -376,7 +406,7 @@ template <class M>
 DNG_HD bool fprep(M &m, const FPlan &F, u32 defmask, double s0, double s1,
     u32 &slow)
 {
-#pragma unroll 1
+DNG_PLAN_LOOP
 	for (u32 j = 0; j < F.ncols; j++) {
 		const Col &col = F.col[j];
 		u32 cw = DNG_FCAP(T_UNDEF, 0, 0, 0);
@@ -488,7 +518,7 @@ template <class M>
 DNG_HD bool fkey_hash(M &m, const FPlan &F, u32 defmask, u32 &hash, u32 &klen)
 {
 	u32 h = 0x2545F491u, kl = 0;
-#pragma unroll 1
+DNG_PLAN_LOOP
 	for (u32 j = 0; j < F.ncols; j++) {
 		FPiece pc;
 		fpiece(m, F, j, defmask, pc);
@@ -527,7 +557,7 @@ template <class M, class K>
 DNG_HD bool fkey_equal(M &m, const FPlan &F, u32 defmask, K &k)
 {
 	u32 o = 0, diff = 0;
-#pragma unroll 1
+DNG_PLAN_LOOP
 	for (u32 j = 0; j < F.ncols; j++) {
 		FPiece pc;
 		fpiece(m, F, j, defmask, pc);
@@ -585,7 +615,7 @@ template <class M>
 DNG_HD void fkey_write(M &m, const FPlan &F, u32 defmask, u8 *out)
 {
 	u32 o = 0;
-#pragma unroll 1
+DNG_PLAN_LOOP
 	for (u32 j = 0; j < F.ncols; j++) {
 		FPiece pc;
 		fpiece(m, F, j, defmask, pc);

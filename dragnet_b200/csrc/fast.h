@@ -60,7 +60,8 @@ struct alignas(16) FPlan {
 	u8 ord_row[F_MAXCOLS];		/* bucketized column j parks its ordinal in
 					 * capture rows ord_row[j], + 1 */
 	u8 nrows;			/* capture rows in all */
-	u8 pad[5];
+	u8 ncode;			/* leaves in code[]; jumps only go forward */
+	u8 pad[4];
 	char pool[F_POOL];
 };
 

@@ -79,7 +79,8 @@ DatasourceGpu.prototype.scan = function (args)
 		return ({ 'name': s.name, 'field': s.field });
 	});
 	bounds = null;
-	if (query.qc_before !== null) {
+	/* (as lib/stream-scan.js:62: either bound asks for the time filter) */
+	if (query.qc_before !== null || query.qc_after !== null) {
 		synthetic.push({ 'name': 'dn_ts', 'field': this.ds_timefield });
 		tf = mod_dragnet_impl.queryTimeBoundsFilter(query, 'dn_ts');
 		bounds = { 'field': 'dn_ts',
@@ -96,7 +97,9 @@ DatasourceGpu.prototype.scan = function (args)
 
 	out = mod_vstream.wrapStream(new mod_stream.PassThrough(
 	    { 'objectMode': true, 'highWaterMark': 0 }), 'Aggregator');
-	scan = dragnet_gpu.scanOpen(plan, this.ds_device);	/* throws on error */
+	/* throws on error; the names label the point fields, in order */
+	scan = dragnet_gpu.scanOpen(plan, this.ds_device,
+	    query.qc_breakdowns.map(function (b) { return (b.name); }));
 
 	/*
 	 * Feed files as they are found.  feedFile() is an N-API async work item:
@@ -124,6 +127,7 @@ DatasourceGpu.prototype.scan = function (args)
 			self.ds_counters = counters;
 			points.forEach(function (p) { out.write(p); });
 			out.end();
+			scan.close();
 		});
 	});
 	return (out);
