@@ -152,6 +152,37 @@ class ClockSampler(object):
             self.proc = None
 
 
+def host_cores():
+    """-> (threads worth starting, description).  os.cpu_count() counts the
+    machine's CPUs; a container may be allowed far fewer (affinity mask, cgroup
+    CPU quota): 128 threads on a 2-CPU quota only add scheduling overhead, and
+    a baseline that says "128 cores" for it misleads."""
+    n = os.cpu_count() or 1
+    why = ['os.cpu_count()=%d' % n]
+    try:
+        a = len(os.sched_getaffinity(0))
+        why.append('affinity=%d' % a)
+        n = min(n, a)
+    except Exception:
+        pass
+    for path, parse in (
+            ('/sys/fs/cgroup/cpu.max',
+             lambda t: None if t.split()[0] == 'max' else
+             float(t.split()[0]) / float(t.split()[1])),
+            ('/sys/fs/cgroup/cpu/cpu.cfs_quota_us',
+             lambda t: None if int(t) <= 0 else int(t) / float(
+                 open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read()))):
+        try:
+            q = parse(open(path).read().strip())
+        except Exception:
+            continue
+        if q:
+            why.append('cgroup quota=%.1f' % q)
+            n = min(n, max(1, int(q + 0.999)))
+        break
+    return max(1, n), ', '.join(why)
+
+
 def canon(points):
     return sorted((tuple(repr(c) for c in cols), v) for cols, v in points)
 
@@ -194,7 +225,7 @@ def sample_file(rows, seed, total_rows, first=0):
     if not os.path.exists(path):
         subprocess.check_call([gen, path + '.tmp', str(seed), str(total_rows),
                                str(first), str(rows),
-                               str(min(32, os.cpu_count() or 1))])
+                               str(min(32, host_cores()[0]))])
         os.rename(path + '.tmp', path)
     return path
 
@@ -244,7 +275,7 @@ def reference_arm(args, rank, world):
         return
     argv, ds, desc = QUERIES[args.query]
     plan = make_plan(argv, ds)
-    threads = os.cpu_count() or 1
+    threads, cores_how = host_cores()
     rows = args.cpu_rows
     path = sample_file(rows, 0xD5A60000, args.rows)
     for _ in range(max(args.warmup, 1)):
@@ -275,7 +306,8 @@ def reference_arm(args, rank, world):
                            'image); bounded sample of the 100M-row workload, '
                            'scanned repeatedly for >= 2 s per step'},
         'cpu_baseline': {'value': value, 'unit': 'records/s',
-                         'cores': threads, 'kind': 'port',
+                         'cores': threads, 'cores_how': cores_how,
+                         'kind': 'port',
                          'one_thread_value': rows1 / one['mean_seconds'],
                          'sample': '%d rows (%.2f GB) of the workload, %d '
                                    'threads, file-range sharded, mean over '
@@ -485,7 +517,7 @@ def gpu_arm(args, rank, local_rank, world):
                 'clocks': clocks, 'last': res}
 
     peak, how = measured_peaks()
-    cpu_threads = max(1, (os.cpu_count() or 1) // world)
+    cpu_threads = max(1, host_cores()[0] // world)
 
     # ---- value: input resident in HBM -------------------------------------------
     R = timed(feed_resident, args.steps, args.warmup)
@@ -632,8 +664,9 @@ def gpu_arm(args, rank, local_rank, world):
     # ---- cpu_baseline on a bounded sample (rank 0, N=1 only) ---------------------
     cpu = None
     if world == 1 and args.cpu_rows > 0:
-        cpu, _ = cpu_baseline(plan, srows, rows, seed, os.cpu_count() or 1,
+        cpu, _ = cpu_baseline(plan, srows, rows, seed, host_cores()[0],
                               args.cpu_seconds)
+        cpu['cores_how'] = host_cores()[1]
 
     n_launch = max(1, R['launches'])
     st = R['last'][2]
