@@ -163,6 +163,28 @@ struct FSmem {
 		c.w1 = lds32(c.wa);
 		return c;
 	}
+	/* aligned words (fscan.cuh) */
+	struct ACur {
+		u32 wa, k;
+		__device__ __forceinline__ u32 next()
+		{
+			const u32 v = lds32(wa);
+			wa += 4;
+			return v;
+		}
+	};
+	__device__ __forceinline__ ACur acursor(u32 off) const
+	{
+		ACur c;
+		const u32 a = ra + off;
+		c.k = a & 3;
+		c.wa = a & ~3u;
+		return c;
+	}
+	__device__ __forceinline__ u32 apos(const ACur &c) const
+	{
+		return c.wa - 4 - ra;
+	}
 	__device__ __forceinline__ u32 byte(u32 off) const { return lds8(ra + off); }
 	__device__ __forceinline__ u32 word(u32 off) const
 	{
@@ -423,6 +445,10 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 			tz[i] = z;
 		if (lane == 0)
 			mbar_init_sa(mbar, 1);
+		/* the quotes after the buffer that end a runaway string scan
+		 * (fscan.cuh) */
+		if (lane < DNG_F_SLACK / 4)
+			sts32(sb + D0 + CHUNK + 4 * lane, 0x22222222u);
 	}
 	__syncthreads();
 
@@ -499,6 +525,9 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 			}
 			for (u32 i = bulk + lane; i < dlen; i += 32)
 				sts8(sb + D0 + i, a.data[g0 + i]);
+			/* (a short last chunk: the sentinel right behind it) */
+			if (dlen < CHUNK && lane < 16)
+				sts8(sb + D0 + dlen + lane, '"');
 			if (bulk || (first && g0)) {
 				mbar_wait_sa(mbar, parity);
 				parity ^= 1;

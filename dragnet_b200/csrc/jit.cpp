@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <set>
@@ -38,6 +39,9 @@ const char *PRELUDE =
 "typedef unsigned int u32;\n"
 "typedef unsigned long long u64;\n"
 "#define DNG_HD __device__ __forceinline__\n"
+"#ifdef DNG_JIT_SHARED_SCAN\n"
+"#define DNG_FSCAN_FN __device__ __noinline__\n"
+"#endif\n"
 "enum { T_UNDEF = 0, T_NULL = 1, T_FALSE = 2, T_TRUE = 3, T_NUM = 4, T_STR = 5 };\n"
 "#define DNG_FCAP(type, off, len, flag) \\\n"
 "	((u32)(off) | ((u32)(len) << 12) | ((u32)(type) << 24) | ((u32)(flag) << 27))\n"
@@ -92,6 +96,19 @@ const char *PRELUDE =
 "		c.w1 = jlds32(c.wa);\n"
 "		return c;\n"
 "	}\n"
+"	struct ACur {\n"
+"		u32 wa, k;\n"
+"		DNG_HD u32 next() { const u32 v = jlds32(wa); wa += 4; return v; }\n"
+"	};\n"
+"	DNG_HD ACur acursor(u32 off) const\n"
+"	{\n"
+"		ACur c;\n"
+"		const u32 a = ra + off;\n"
+"		c.k = a & 3;\n"
+"		c.wa = a & ~3u;\n"
+"		return c;\n"
+"	}\n"
+"	DNG_HD u32 apos(const ACur &c) const { return c.wa - 4 - ra; }\n"
 "	DNG_HD u32 byte(u32 off) const { return jlds8(ra + off); }\n"
 "	DNG_HD u32 word(u32 off) const { Cur c = cursor(off); return c.next(); }\n"
 "};\n";
@@ -124,6 +141,14 @@ void appendf(std::string &s, const char *fmt, ...)
  * the blocks carries every lane along its own path, and the lanes of a warp
  * meet again in front of every block (a __syncwarp(): the function is called
  * by all 32 lanes, with `active` clear for those without a record).
+ *
+ * A string wildcard takes its closing quote with it (the literals that follow
+ * one lose their first byte), so that what follows `"caller":"x"` and
+ * `"caller":null` is the same text; a block whose only way on is a block
+ * nothing else leads to continues with that block's body (no meeting needed
+ * where nobody can join); literals short enough for the slack behind the
+ * buffer are compared without asking whether the record is that long (its
+ * '\n' differs from every literal byte).
  *
  * Equivalent subtrees are emitted once: records that differ in an optional
  * field take different blocks for it and the same blocks again for what
@@ -223,6 +248,11 @@ std::string jit_source(const u8 *blob, size_t bytes, const FPlan *plan,
 {
 	std::string s;
 	s += "/* generated by libdragnet_gpu (jit.cpp) */\n";
+	/* one copy of each scanner, called (DNG_JIT_SHARED=0: inlined into
+	 * every block) */
+	const char *sh = getenv("DNG_JIT_SHARED");
+	if (!prelude && !(sh && atoi(sh) == 0))
+		s += "#define DNG_JIT_SHARED_SCAN\n";
 	s += prelude ? prelude : PRELUDE;
 	if (plan)
 		plan_source(*plan, s);
@@ -246,6 +276,7 @@ std::string jit_source(const u8 *blob, size_t bytes, const FPlan *plan,
 	};
 	const u32 N = h.nnodes;
 	std::vector<JN> nd(N);
+	bool str_takes_quote = false;
 	for (u32 i = 0; i < N; i++) {
 		const TNode &t = tn[i];
 		JN &n = nd[i];
@@ -274,6 +305,36 @@ std::string jit_source(const u8 *blob, size_t bytes, const FPlan *plan,
 			for (auto &kv : ent)
 				n.disp.push_back(kv);
 		}
+	}
+	/* a string takes its closing quote with it */
+	{
+		std::vector<int> succ;
+		bool okq = true;
+		std::vector<char> strip(N, 0);
+		for (u32 i = 0; i < N && okq; i++) {
+			if (nd[i].kind != TK_STR)
+				continue;
+			if (nd[i].leaf) {	/* (cannot be: a string ends in '"') */
+				okq = false;
+				break;
+			}
+			successors(nd[i], succ);
+			for (int c0 : succ)
+				for (int c = c0; c >= 0; c = nd[c].alt) {
+					if (nd[c].lit.empty() || nd[c].lit[0] != '"')
+						okq = false;
+					strip[c] = 1;
+				}
+			if (nd[i].has_disp && nd[i].dk == 0)
+				okq = false;
+		}
+		for (u32 i = 0; i < N && okq; i++) {
+			if (strip[i])
+				nd[i].lit.erase(0, 1);
+			if (nd[i].kind == TK_STR && nd[i].has_disp)
+				nd[i].dk--;
+		}
+		str_takes_quote = okq;
 	}
 	/* do the captures along every way to a leaf add up to its mask? */
 	bool accumulate = true;
@@ -363,25 +424,42 @@ std::string jit_source(const u8 *blob, size_t bytes, const FPlan *plan,
 		}
 	}
 	const u32 FAIL = 0xffffu, DONE = 0xfffeu;
-	appendf(s, "	u32 st = active ? %uu : %uu;\n", (u32)canon[0], FAIL);
-	for (u32 i = 0; i < N; i++) {
-		if (!live[i])
-			continue;
+	/* who leads to whom (over the blocks that are emitted) */
+	std::vector<u32> indeg(N, 0);
+	std::vector<char> alt_target(N, 0);
+	{
+		std::vector<int> succ;
+		for (u32 i = 0; i < N; i++) {
+			if (!live[i])
+				continue;
+			if (nd[i].alt >= 0) {
+				indeg[canon[nd[i].alt]]++;
+				alt_target[canon[nd[i].alt]] = 1;
+			}
+			successors(nd[i], succ);
+			for (int c : succ)
+				indeg[canon[c]]++;
+		}
+		indeg[canon[0]]++;
+	}
+	/* may block v's body follow its only predecessor's in place? */
+	auto inlinable = [&](int v) {
+		return indeg[v] == 1 && !alt_target[v] && nd[v].alt < 0;
+	};
+	std::vector<char> emitted(N, 0);
+	/* the body of node i (inside a do { } while (0) that a mismatch breaks
+	 * out of), then what follows it */
+	std::function<void(u32, bool)> body = [&](u32 i, bool head) {
 		const JN &n = nd[i];
 		const u32 L = (u32)n.lit.size();
-		const u32 onfail = n.alt < 0 ? FAIL : (u32)canon[n.alt];
-		/* every lane of the warp is here (jump threading would
-		 * otherwise keep apart the lanes that arrive from different
-		 * blocks, all the way to the end) */
-		s += "	__syncwarp();\n";
-		appendf(s, "	if (st == %uu) {\n		st = %uu;\n", i, onfail);
-		/* the body runs inside do { } while (0): a mismatch breaks out
-		 * with st = the alt sibling / FAIL */
-		s += "		do {\n";
+		emitted[i] = 1;
+		appendf(s, "			/* node %u */\n", i);
 		if (L) {
-			appendf(s, "			if (p + %uu > len)\n"
-			    "				break;\n", L);
-			s += "			const u32 a_ = ra + p, sh = (a_ & 3) * 8, "
+			/* (longer than the slack behind the buffer: ask) */
+			if (L > 48)
+				appendf(s, "			if (p + %uu > len)\n"
+				    "				break;\n", L);
+			s += "			{\n			const u32 a_ = ra + p, sh = (a_ & 3) * 8, "
 			    "wa = a_ & ~3u;\n			u32 w0 = jlds32(wa), w1, "
 			    "diff;\n";
 			const u32 nw = (L + 3) / 4;
@@ -403,17 +481,20 @@ std::string jit_source(const u8 *blob, size_t bytes, const FPlan *plan,
 					appendf(s, "__funnelshift_r(%s, %s, sh) ^ "
 					    "0x%08xu;\n", lo, hi, lit);
 			}
-			s += "			if (diff)\n				break;\n";
+			s += "			if (diff)\n				break;\n			}\n";
 			appendf(s, "			q = p + %uu;\n", L);
 		} else {
 			s += "			q = p;\n";
 		}
-		if (n.kind == TK_STR)
+		if (n.kind == TK_STR) {
 			s += "			if (!fscan_str(m, q, val))\n"
 			    "				break;\n";
-		else if (n.kind == TK_BARE)
+			if (str_takes_quote)
+				s += "			q++;\n";
+		} else if (n.kind == TK_BARE) {
 			s += "			if (!fscan_bare(m, q, val))\n"
 			    "				break;\n";
+		}
 		if (n.cap) {
 			appendf(s, "			jsts32(caps + %uu, val);\n",
 			    (u32)(n.cap - 1) * 768u * 4u);
@@ -433,17 +514,43 @@ std::string jit_source(const u8 *blob, size_t bytes, const FPlan *plan,
 				    1u | (n.leaf_mask << 1));
 		} else if (n.has_disp) {
 			appendf(s, "			st = %uu;\n", FAIL);
-			appendf(s, "			if (p + %uu >= len)\n"
-			    "				break;\n", n.dk);
-			appendf(s, "			const u32 db = m.byte(p + %uu);\n",
-			    n.dk);
+			if (n.dk > 48)
+				appendf(s, "			if (p + %uu >= len)\n"
+				    "				break;\n", n.dk);
+			appendf(s, "			const u32 db%u = m.byte(p + %uu);\n",
+			    i, n.dk);
 			for (auto &d : n.disp)
-				appendf(s, "			if (db == %uu)\n"
-				    "				st = %uu;\n", d.first,
+				appendf(s, "			if (db%u == %uu)\n"
+				    "				st = %uu;\n", i, d.first,
 				    (u32)canon[d.second]);
 		} else {
-			appendf(s, "			st = %uu;\n", (u32)canon[n.next]);
+			const int nx = canon[n.next];
+			if (inlinable(nx) && !emitted[nx]) {
+				/* (a later mismatch fails the record, whatever
+				 * sibling this block had) */
+				if (head && n.alt >= 0)
+					appendf(s, "			st = %uu;\n", FAIL);
+				body((u32)nx, false);
+			} else {
+				appendf(s, "			st = %uu;\n", (u32)nx);
+			}
 		}
+	};
+	appendf(s, "	u32 st = active ? %uu : %uu;\n", (u32)canon[0], FAIL);
+	for (u32 i = 0; i < N; i++) {
+		if (!live[i] || emitted[i])
+			continue;
+		const JN &n = nd[i];
+		const u32 onfail = n.alt < 0 ? FAIL : (u32)canon[n.alt];
+		/* every lane of the warp is here (jump threading would
+		 * otherwise keep apart the lanes that arrive from different
+		 * blocks, all the way to the end) */
+		s += "	__syncwarp();\n";
+		appendf(s, "	if (st == %uu) {\n		st = %uu;\n", i, onfail);
+		/* the body runs inside do { } while (0): a mismatch breaks out
+		 * with st = the alt sibling / FAIL */
+		s += "		do {\n";
+		body(i, true);
 		s += "		} while (0);\n	}\n";
 	}
 	s += "	return res;\n}\n";

@@ -282,7 +282,8 @@ DNG_HD bool tmpl_match(M &m, u32 len, RecState &R, bool active)
 }
 
 #ifndef __CUDACC__
-/* host access (tests/hostcheck only): plain memory, '\n' past the record */
+/* host access (tests/hostcheck only): plain memory; past the record a '\n',
+ * then quotes (fscan.cuh: what the kernel's buffers guarantee) */
 struct TmplHostMem {
 	const u8 *rec;
 	u32 len;
@@ -293,7 +294,18 @@ struct TmplHostMem {
 		u32 off;
 		u32 next() { u32 w = m->word(off); off += 4; return w; }
 	};
-	u32 byte(u32 off) const { return off < len ? rec[off] : (u32)'\n'; }
+	struct ACur {
+		const TmplHostMem *m;
+		u32 off, k;
+		u32 next() { u32 w = m->word(off); off += 4; return w; }
+	};
+	ACur acursor(u32 off) const {
+		ACur c; c.m = this; c.k = off & 3; c.off = off - c.k; return c;
+	}
+	u32 apos(const ACur &c) const { return c.off - 4; }
+	u32 byte(u32 off) const {
+		return off < len ? rec[off] : off == len ? (u32)'\n' : (u32)'"';
+	}
 	u32 word(u32 off) const {
 		return byte(off) | (byte(off + 1) << 8) | (byte(off + 2) << 16) |
 		    (byte(off + 3) << 24);

@@ -65,6 +65,9 @@ static const char *HOST_PRELUDE =
 "		u32 next() { const u32 d = __funnelshift_r(w0, w1, sh); w0 = w1; wa += 4; w1 = jlds32(wa); return d; } };\n"
 "	Cur cursor(u32 off) const { Cur c; const u32 a = ra + off; c.sh = (a & 3) * 8; c.wa = (a & ~3u) + 4;\n"
 "		c.w0 = jlds32(c.wa - 4); c.w1 = jlds32(c.wa); return c; }\n"
+"	struct ACur { u32 wa, k; u32 next() { const u32 v = jlds32(wa); wa += 4; return v; } };\n"
+"	ACur acursor(u32 off) const { ACur c; const u32 a = ra + off; c.k = a & 3; c.wa = a & ~3u; return c; }\n"
+"	u32 apos(const ACur &c) const { return c.wa - 4 - ra; }\n"
 "	u32 byte(u32 off) const { return jlds8(ra + off); }\n"
 "	u32 word(u32 off) const { Cur c = cursor(off); return c.next(); }\n};\n";
 
@@ -231,10 +234,12 @@ int main(int argc, char **argv)
 			bool matched;
 			if (jm) {
 				/* the record at an odd address of the fake shared
-				 * memory, '\n' after it, captures in rows of 768 */
+				 * memory, '\n' and the sentinel quotes after it,
+				 * captures in rows of 768 */
 				const u32 ra = 1027, caps = 32768;
 				memcpy(jbuf + ra, rec, len);
-				memset(jbuf + ra + len, '\n', 64);
+				jbuf[ra + len] = '\n';
+				memset(jbuf + ra + len + 1, '"', 64);
 				const unsigned r = jm(ra, len, 1, caps);
 				matched = r & 1;
 				defmask = r >> 1;
