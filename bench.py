@@ -42,25 +42,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
+def _bd(*fields):
+    return [dict(f) if isinstance(f, dict) else {'name': f, 'field': f}
+            for f in fields]
+
+
+# (query configuration as `dn scan` builds it from its arguments
+# (bin/dn:696-724), datasource config, what BASELINE.json calls it, the
+# arguments for the record)
 QUERIES = {
-    'C2': (['-b', 'req.method'], None,
-           'configs[1]: 100M-row synthetic NDJSON, -b req.method'),
-    'C3': (['-b', 'req.method,res.statusCode', '-f',
-            '{"eq":["req.method","GET"]}'], None,
-           'configs[2]: 100M rows, -b req.method,res.statusCode + krill eq'),
-    'C4': (['-b', 'latency[aggr=quantize]'], None,
-           'configs[3]: -b latency[aggr=quantize] numeric histogram'),
-    'C5': (['-b', 'operation,req.method,host'], None,
-           'configs[4]: 3-key breakdown, NCCL final reduce'),
+    'C2': ({'breakdowns': _bd('req.method')}, None,
+           'configs[1]: 100M-row synthetic NDJSON, -b req.method',
+           '-b req.method'),
+    'C3': ({'breakdowns': _bd('req.method', 'res.statusCode'),
+            'filter': {'eq': ['req.method', 'GET']}}, None,
+           'configs[2]: 100M rows, -b req.method,res.statusCode + krill eq',
+           '-b req.method,res.statusCode -f {"eq":["req.method","GET"]}'),
+    'C4': ({'breakdowns': _bd({'name': 'latency', 'field': 'latency',
+                               'aggr': 'quantize'})}, None,
+           'configs[3]: -b latency[aggr=quantize] numeric histogram',
+           '-b latency[aggr=quantize]'),
+    'C5': ({'breakdowns': _bd('operation', 'req.method', 'host')}, None,
+           'configs[4]: 3-key breakdown, NCCL final reduce',
+           '-b operation,req.method,host'),
 }
 
 
-def make_plan(argv, ds=None):
-    from dragnet_b200 import dn as mod_dn
+def make_plan(qconf, ds=None):
     from dragnet_b200 import query as mod_query
     ds = ds or {}
-    options = mod_dn.dnParseArgs(list(argv))
-    q = mod_dn.dnQueryConfig(options)['query']
+    q = mod_query.queryLoad({'query': qconf})
+    if isinstance(q, Exception):
+        raise q
     return mod_query.scan_plan(q, ds_filter=ds.get('filter'),
                                time_field=ds.get('timeField'))
 
@@ -273,8 +286,8 @@ def reference_arm(args, rank, world):
     at least two seconds.  Nothing of the product library is loaded."""
     if rank != 0:
         return
-    argv, ds, desc = QUERIES[args.query]
-    plan = make_plan(argv, ds)
+    qconf, ds, desc, _ = QUERIES[args.query]
+    plan = make_plan(qconf, ds)
     threads, cores_how = host_cores()
     rows = args.cpu_rows
     path = sample_file(rows, 0xD5A60000, args.rows)
@@ -299,7 +312,7 @@ def reference_arm(args, rank, world):
         'data': 'synthetic',
         'config': {'workload': desc, 'rows_per_scan': rows,
                    'scans_per_step': reps / float(args.steps),
-                   'query': ' '.join(argv),
+                   'query': QUERIES[args.query][3],
                    'note': 'CPU reference arm: C++ restatement of the '
                            'reference Node.js scan path (node and the '
                            "reference's npm dependencies are not in this "
@@ -363,8 +376,8 @@ def gpu_arm(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', dev))
     L = native.lib()
-    argv, ds, desc = QUERIES[args.query]
-    plan = make_plan(argv, ds)
+    qconf, ds, desc, _ = QUERIES[args.query]
+    plan = make_plan(qconf, ds)
     rows = args.rows
     seed = 0xD5A60000 + rank
     # clocks / throttle reasons of every GPU of the job, sampled by rank 0 from
@@ -416,7 +429,7 @@ def gpu_arm(args, rank, local_rank, world):
 
     def plan_handle(q):
         if q not in handles:
-            a, d, _ = QUERIES[q]
+            a, d = QUERIES[q][:2]
             handles[q] = native.Plan(json.dumps(make_plan(a, d),
                                                 separators=(',', ':')))
         return handles[q]
@@ -539,7 +552,7 @@ def gpu_arm(args, rank, local_rank, world):
     # ---- what the oracle says about this rank's pool and about a sample ------
     # (every rank checks its own shard; the oracle's threads are shared out)
     def oracle_tallies(q, path):
-        a, d, _ = QUERIES[q]
+        a, d = QUERIES[q][:2]
         doc = run_oracle(make_plan(a, d), path, cpu_threads)
         return {tuple(repr(c) for c in cols): v
                 for cols, v in oracle_points(doc)}, doc
@@ -584,7 +597,7 @@ def gpu_arm(args, rank, local_rank, world):
         cms = C['dev_ms'] / steps
         gbs = (C['kernel_bytes'] / 1e9) / (C['kernel_ms'] / 1e3)
         configs.append({
-            'config': QUERIES[q][2], 'query': ' '.join(QUERIES[q][0]),
+            'config': QUERIES[q][2], 'query': QUERIES[q][3],
             'rows_per_gpu': rows, 'value': total_rows / (cms / 1e3),
             'unit': 'records/s', 'ms_per_step': cms,
             'kernel': kernel_name(C['last'][2]),
@@ -702,7 +715,7 @@ def gpu_arm(args, rank, local_rank, world):
         'dtype': 'u8', 'data': 'synthetic',
         'config': {
             'workload': desc, 'rows_per_gpu': rows,
-            'bytes_per_gpu': nbytes, 'query': ' '.join(argv),
+            'bytes_per_gpu': nbytes, 'query': QUERIES[args.query][3],
             'parallelism': 'shard-per-gpu x%d, one NCCL reduce of the '
                            'tallies' % world if world > 1 else 'single gpu',
             'l2': 'inputs (%.1f GB) >> L2 (126 MB): no flush needed' %

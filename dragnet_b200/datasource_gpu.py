@@ -12,7 +12,6 @@ files.  build/query/index* are outside the GPU hot path
 and raise NotImplementedError.
 """
 
-from . import find as mod_find
 from . import native
 from . import query as mod_query
 
@@ -47,8 +46,8 @@ def stage_counters(plan, c, npoints):
         put('SkinnerAdapterStream', 'ninputs', n)
         put('SkinnerAdapterStream', 'noutputs', n)
     else:
-        put('json parser', 'invalid point', c['invalid_point'])
-        n -= c['invalid_point']
+        put('json parser', 'invalid point', c.get('invalid_point', 0))
+        n -= c.get('invalid_point', 0)
 
     def filt(stage, present, kf, ke):
         nonlocal n
@@ -72,6 +71,10 @@ def stage_counters(plan, c, npoints):
         put('Datetime parser', 'noutputs', n)
     filt('Time filter', plan.get('time_bounds'), 'time_filtered',
          'time_failedeval')
+    # (what is left must be what the aggregator counted)
+    naggr = c.get('aggr_ninputs', c.get('aggr'))
+    if naggr is not None and n != naggr:
+        raise DsError('stage counters do not add up: %r' % (c,))
     put('Aggregator', 'ninputs', n)
     put('Aggregator', 'noutputs', npoints)
     return out
@@ -136,6 +139,10 @@ class DatasourceGpu(object):
         self.ds_datapath = bc.get('path')
         self.ds_filter = dsconfig.get('filter') or None
         self.ds_device = dsconfig.get('device', 0)
+        # (root, timeFormat, after_ms, before_ms) -> [paths]: the reference's
+        # own enumeration (lib/datasource-file.js:218-246 findStream), which
+        # the real integration keeps; the tests pass their mirror of it
+        self.ds_find = args.get('findFiles')
 
     def close(self):
         pass
@@ -151,8 +158,10 @@ class DatasourceGpu(object):
                            'and "after" constraints')
         if self.ds_format not in ('json', 'json-skinner'):
             return DsError('unsupported format: "%s"' % self.ds_format)
-        files = mod_find.find_files(self.ds_datapath, self.ds_timeformat,
-                                    query.qc_after, query.qc_before)
+        if self.ds_find is None:
+            return DsError('no file enumerator ("findFiles")')
+        files = self.ds_find(self.ds_datapath, self.ds_timeformat,
+                             query.qc_after, query.qc_before)
         if dry:
             return ScanResult([], {}, files)
         plan = mod_query.scan_plan(query, ds_filter=self.ds_filter,
@@ -170,8 +179,10 @@ class DatasourceGpu(object):
         if self.ds_timefield is None and (args['interval'] != 'all' or
                                           after or before):
             return DsError('datasource is missing "timefield"')
-        files = mod_find.find_files(self.ds_datapath, self.ds_timeformat,
-                                    after, before)
+        if self.ds_find is None:
+            return DsError('no file enumerator ("findFiles")')
+        files = self.ds_find(self.ds_datapath, self.ds_timeformat,
+                             after, before)
         if args.get('dryRun'):
             return ScanResult([], {}, files)
         queries = [mod_query.metricQuery(m, after, before, args['interval'],

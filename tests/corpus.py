@@ -6,7 +6,7 @@ tests/golden)."""
 import json
 import random
 
-from dragnet_b200 import dn as mod_dn
+from hostmirror import dn as mod_dn
 from dragnet_b200 import query as mod_query
 
 # ---------------------------------------------------------------------------

@@ -8,8 +8,8 @@ point shape: ([(name, bytes|float), ...], value).
 
 import os
 
-from dragnet_b200 import dn as mod_dn
-from dragnet_b200 import find as mod_find
+from hostmirror import dn as mod_dn
+from hostmirror import find as mod_find
 from dragnet_b200 import query as mod_query
 
 OUR_STAGES = set(mod_dn.STAGE_ORDER) | {'Flattener'}

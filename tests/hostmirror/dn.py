@@ -12,16 +12,19 @@ Host-side mirror of the scan-related parts of the reference CLI:
   lib/skinner-flattener.js (re-aggregation into flat rows)
 
 The CLI itself is out of scope of the GPU hot path: this
-module never touches record data, only the <= #tuples points a scan emits.
+module never touches record data, only the <= #tuples points a scan emits.  It
+is TEST INFRASTRUCTURE (the harness that replays the reference's golden
+files), not part of the product package.
 """
 
 import json
 import math
 import sys
 
-from . import jsdate
-from . import query as mod_query
+from dragnet_b200 import jsdate
+from dragnet_b200 import query as mod_query
 from .attr_parser import attrsParse
+from . import find as mod_find
 
 
 class UsageError(Exception):
@@ -453,7 +456,7 @@ def render_scan(query, options, points, title='datasource'):
 def main(argv=None, datasources=None, out=None, err=None):
     """`dn scan [opts] DATASOURCE` against an in-memory datasource table:
     ``datasources`` maps name -> dsconfig dict (see datasource_gpu)."""
-    from . import datasource_gpu
+    from dragnet_b200 import datasource_gpu
     argv = list(sys.argv[1:] if argv is None else argv)
     out = out or sys.stdout
     err = err or sys.stderr
@@ -476,7 +479,8 @@ def main(argv=None, datasources=None, out=None, err=None):
         if not datasources or dsname not in datasources:
             raise FatalError('unknown datasource: "%s"' % dsname)
         ds = datasource_gpu.datasourceForConfig(
-            {'dsconfig': datasources[dsname]})
+            {'dsconfig': datasources[dsname],
+             'findFiles': mod_find.find_files})
         if isinstance(ds, Exception):
             raise FatalError(str(ds))
         scanargs = dnQueryConfig(options)

@@ -1,4 +1,6 @@
-"""Input enumeration for the file-backed GPU datasource.
+"""Input enumeration for the file-backed GPU datasource (test infrastructure:
+the real integration keeps the reference's own scanInit enumeration and hands
+the file list to the addon, integration/datasource-gpu.js).
 
 Host-side mirror of ``DatasourceFile.findStream`` (lib/datasource-file.js:218-246):
 a recursive, name-sorted file walk (lib/fs-find.js) optionally pruned by a
@@ -10,7 +12,7 @@ pattern, then step by that unit while < end).  SURVEY.md section 8(f) rank 4.
 import os
 import stat
 
-from . import jsdate
+from dragnet_b200 import jsdate
 
 
 def path_enumerate(pattern, start_ms, end_ms):

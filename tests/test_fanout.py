@@ -90,9 +90,11 @@ def test_index_scan_datasource(datadir):
     """DatasourceGpu.indexScan mirrors the reference's build scan: hourly
     __dn_ts buckets are prepended unless interval is 'all'."""
     from dragnet_b200 import datasource_gpu
+    from hostmirror import find as mod_find
     ds = datasource_gpu.datasourceForConfig({'dsconfig': {
         'backend': 'gpu', 'backend_config': {
-            'path': datadir, 'timeFormat': '%Y/%m-%d', 'timeField': 'time'}}})
+            'path': datadir, 'timeFormat': '%Y/%m-%d', 'timeField': 'time'}},
+        'findFiles': mod_find.find_files})
     res = ds.indexScan({'metrics': METRICS[:2], 'interval': 'day',
                         'dryRun': False})
     total = [(f, v) for f, v in res.points if f[-1][1] == 0]

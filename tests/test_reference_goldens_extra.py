@@ -22,7 +22,7 @@ import pytest
 sys.path.insert(0, os.path.dirname(__file__))
 from engines import cpp_engine, hostcheck_engine, py_engine  # noqa: E402
 
-from dragnet_b200 import dn as mod_dn  # noqa: E402
+from hostmirror import dn as mod_dn  # noqa: E402
 from dragnet_b200 import query as mod_query  # noqa: E402
 
 
