@@ -461,15 +461,15 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 template <int NSL>
 void launch_fkernel(dng_scan *s, const FScanArgs &a, u32 grid)
 {
-	scan_kernel_f<NSL><<<grid, DNG_NT, fkernel_smem<NSL>(a.tmpl_bytes,
+	scan_kernel_f<NSL><<<grid, DNG_F_NT, fkernel_smem<NSL>(a.tmpl_bytes,
 	    a.s1slots, a.sslots, a.nrows), s->stream>>>(a);
 }
 
 /* tally-cache sizes of the F kernel: what its buffers leave */
 template <int NSL>
-void fkernel_slots(const dng_scan *s, u32 nrows, u32 *s1, u32 *s2)
+void fkernel_slots(const dng_scan *s, u32 nrows, u32 tmpl_room, u32 *s1, u32 *s2)
 {
-	const size_t fixed = fkernel_smem<NSL>(TMPL_RESERVE, 0, 0, nrows);
+	const size_t fixed = fkernel_smem<NSL>(tmpl_room, 0, 0, nrows);
 	const size_t room = s->f_smem_max > fixed ? s->f_smem_max - fixed : 0;
 	u32 n1 = 32;
 	while (n1 < 1024 && (size_t)n1 * 2 * sizeof (SSlot1) +
@@ -522,11 +522,11 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 	const u32 nsl = s->f_nsl;
 	const unsigned long long chunk = 32ull * 16 * nsl;
 	a.nchunks = (u32)((nbytes + chunk - 1) / chunk);
-	const u32 grid = std::min<u32>((a.nchunks + DNG_NW - 1) / DNG_NW,
+	const u32 grid = std::min<u32>((a.nchunks + DNG_F_NW - 1) / DNG_F_NW,
 	    (u32)s->sm_count);
 	/* segments: long enough to amortise the pre-lap, short enough to keep
 	 * every warp of the grid busy */
-	const u32 nwarps = grid * DNG_NW;
+	const u32 nwarps = grid * DNG_F_NW;
 	a.seg = std::max<u32>(1, std::min<u32>(DNG_F_SEG,
 	    a.nchunks / (nwarps * 8)));
 	/* the segment queue: [1] of the miss counter's allocation */
@@ -536,28 +536,33 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 	cudaEventRecord(e0, s->stream);
 	/* the matcher compiled for these templates, once it is there */
 	const bool jit = s->jit && s->jit->state.load() == 1 && s->ftmpl_bytes;
+	/* (the compiled matcher has the templates in its code: no trie in shared
+	 * memory, more of it for the tally cache) */
+	const u32 tmpl_room = jit ? 0 : (u32)TMPL_RESERVE;
+	if (jit)
+		a.tmpl_bytes = 0;
 	size_t smem = 0;
 	switch (nsl) {
 	case 7:
-		fkernel_slots<7>(s, a.nrows, &a.s1slots, &a.sslots);
+		fkernel_slots<7>(s, a.nrows, tmpl_room, &a.s1slots, &a.sslots);
 		smem = fkernel_smem<7>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
 		if (!jit)
 			launch_fkernel<7>(s, a, grid);
 		break;
 	case 9:
-		fkernel_slots<9>(s, a.nrows, &a.s1slots, &a.sslots);
+		fkernel_slots<9>(s, a.nrows, tmpl_room, &a.s1slots, &a.sslots);
 		smem = fkernel_smem<9>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
 		if (!jit)
 			launch_fkernel<9>(s, a, grid);
 		break;
 	case 11:
-		fkernel_slots<11>(s, a.nrows, &a.s1slots, &a.sslots);
+		fkernel_slots<11>(s, a.nrows, tmpl_room, &a.s1slots, &a.sslots);
 		smem = fkernel_smem<11>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
 		if (!jit)
 			launch_fkernel<11>(s, a, grid);
 		break;
 	default:
-		fkernel_slots<13>(s, a.nrows, &a.s1slots, &a.sslots);
+		fkernel_slots<13>(s, a.nrows, tmpl_room, &a.s1slots, &a.sslots);
 		smem = fkernel_smem<13>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
 		if (!jit)
 			launch_fkernel<13>(s, a, grid);
@@ -567,7 +572,7 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 	if (jit) {
 		void *args[] = { &a };
 		le = cudaLaunchKernel((const void *)s->jit->kern, dim3(grid),
-		    dim3(DNG_NT), args, smem, s->stream);
+		    dim3(DNG_F_NT), args, smem, s->stream);
 		s->jit_launches++;
 	}
 	if (le == cudaSuccess)
@@ -657,6 +662,11 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 			s->learn_tmpl = lv[CTR_TMPL];
 		}
 	}
+	/* (a plan with many capture rows leaves the F kernel's buffers no room) */
+	if (s->f_kernel && s->fplan.ok &&
+	    fkernel_smem<13>(TMPL_RESERVE, 32, DNG_SSLOTS_MIN, s->fplan.nrows) >
+	    s->f_smem_max)
+		s->f_kernel = false;
 	if (s->f_kernel && s->fplan.ok)
 		return launch_fscan(s, data, start, nbytes, final);
 	ScanArgs a;

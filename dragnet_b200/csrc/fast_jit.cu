@@ -18,7 +18,7 @@ using namespace dng;
 #define DNG_JIT_NSL 13
 #endif
 
-extern "C" __global__ void __launch_bounds__(DNG_NT, 1)
+extern "C" __global__ void __launch_bounds__(DNG_F_NT, 1)
 dng_scan_kernel_j(const FScanArgs a)
 {
 	fscan_body<DNG_JIT_NSL, true>(a);

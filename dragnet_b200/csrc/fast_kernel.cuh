@@ -3,7 +3,7 @@
  * scan_miss_kernel, which hands the records it did not take to the general
  * per-record code.
  *
- * Geometry: one persistent 768-thread CTA per SM; every WARP is its own
+ * Geometry: one persistent 896-thread CTA per SM; every WARP is its own
  * pipeline, as in scan_kernel_w, over SEGMENTS of consecutive chunks:
  *
  *   - a chunk is 32 lane slices of NSL x 16 bytes (the host picks NSL so that
@@ -37,6 +37,8 @@
 
 namespace dng {
 
+#define DNG_F_NT F_NT			/* threads per CTA */
+#define DNG_F_NW (DNG_F_NT / 32)
 #define DNG_F_PRE 512			/* pre-lap bytes = longest straddling head */
 #define DNG_F_SLACK 64
 #define DNG_F_NLCAP 128			/* newline positions per chunk */
@@ -84,8 +86,8 @@ static inline size_t fkernel_smem(u32 tmpl_bytes, u32 s1slots, u32 sslots,
     u32 nrows)
 {
 	return FPLAN_SMEM + tmpl_bytes + (size_t)s1slots * sizeof (SSlot1) +
-	    (size_t)sslots * sizeof (SSlot) + (size_t)nrows * DNG_NT * 4 +
-	    (size_t)DNG_NW * FWarpSmem<NSL>::BYTES;
+	    (size_t)sslots * sizeof (SSlot) + (size_t)nrows * DNG_F_NT * 4 +
+	    (size_t)DNG_F_NW * FWarpSmem<NSL>::BYTES;
 }
 
 /* mbarrier / TMA helpers on 32-bit shared addresses (no generic pointers to
@@ -207,11 +209,11 @@ struct FSmem {
 	__device__ __forceinline__ u32 pool32(u32 off) const { return lds32(pool + off); }
 	__device__ __forceinline__ void setcap(u32 p, u32 v) const
 	{
-		sts32(caps + p * (DNG_NT * 4), v);
+		sts32(caps + p * (DNG_F_NT * 4), v);
 	}
 	__device__ __forceinline__ u32 getcap(u32 p) const
 	{
-		return lds32(caps + p * (DNG_NT * 4));
+		return lds32(caps + p * (DNG_F_NT * 4));
 	}
 };
 
@@ -418,7 +420,7 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 	stab.mask1 = a.s1slots - 1;
 	stab.mask = a.sslots - 1;
 	const u32 caps_sa = smem_u32(sp);
-	sp += a.nrows * DNG_NT * 4;
+	sp += a.nrows * DNG_F_NT * 4;
 
 	const u32 tid = threadIdx.x;
 	const u32 lane = tid & 31, wid = tid >> 5;
@@ -431,17 +433,17 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 	{	/* plan, templates -> shared; clear the tally cache */
 		const uint4 *src = (const uint4 *)a.fplan;
 		uint4 *dst = (uint4 *)smem;
-		for (u32 i = tid; i < FPLAN_SMEM / 16; i += DNG_NT)
+		for (u32 i = tid; i < FPLAN_SMEM / 16; i += DNG_F_NT)
 			dst[i] = src[i];
 		const uint4 *tsrc = (const uint4 *)a.tmpl;
 		uint4 *tdst = (uint4 *)(smem + FPLAN_SMEM);
-		for (u32 i = tid; i < a.tmpl_bytes / 16; i += DNG_NT)
+		for (u32 i = tid; i < a.tmpl_bytes / 16; i += DNG_F_NT)
 			tdst[i] = tsrc[i];
 		const uint4 z = make_uint4(0, 0, 0, 0);
 		uint4 *tz = (uint4 *)stab.s1;
 		const u32 tab_bytes = a.s1slots * (u32)sizeof (SSlot1) +
 		    a.sslots * (u32)sizeof (SSlot);
-		for (u32 i = tid; i < tab_bytes / 16; i += DNG_NT)
+		for (u32 i = tid; i < tab_bytes / 16; i += DNG_F_NT)
 			tz[i] = z;
 		if (lane == 0)
 			mbar_init_sa(mbar, 1);
@@ -475,7 +477,7 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 	 * at the final barrier).  The first round is implicit -- warp gw takes
 	 * segment gw, spread over the SMs -- the counter hands out the rest.
 	 */
-	const u32 nwarps = gridDim.x * DNG_NW;
+	const u32 nwarps = gridDim.x * DNG_F_NW;
 	const u32 gw = wid * gridDim.x + blockIdx.x;
 	const u32 nseg = (a.nchunks + a.seg - 1) / a.seg;
 
@@ -806,7 +808,7 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 
 #ifndef DNG_JIT_HOT
 template <int NSL>
-__global__ void __launch_bounds__(DNG_NT, 1)
+__global__ void __launch_bounds__(DNG_F_NT, 1)
 scan_kernel_f(const FScanArgs a)
 {
 	fscan_body<NSL, false>(a);

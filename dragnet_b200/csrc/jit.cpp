@@ -500,7 +500,7 @@ std::string jit_source(const u8 *blob, size_t bytes, const FPlan *plan,
 		}
 		if (n.cap) {
 			appendf(s, "			jsts32(caps + %uu, val);\n",
-			    (u32)(n.cap - 1) * 768u * 4u);
+			    (u32)(n.cap - 1) * (u32)F_NT * 4u);
 			if (accumulate)
 				appendf(s, "			dm |= 0x%xu;\n",
 				    1u << (n.cap - 1));
@@ -665,6 +665,11 @@ double now_ms()
 
 } /* namespace */
 
+bool jit_prepare()
+{
+	return libs().ok;
+}
+
 bool jit_build(const std::string &source, int nsl, std::string &cubin,
     std::string &err, double *compile_ms, double *link_ms)
 {
@@ -683,6 +688,11 @@ bool jit_build(const std::string &source, int nsl, std::string &cubin,
 		err = "no kernel for this slice size";
 		return false;
 	}
+	/* one build at a time: two links running side by side (scans started in
+	 * quick succession, each with its compiler thread) have crashed inside
+	 * libnvJitLink */
+	static std::mutex build_mu;
+	std::lock_guard<std::mutex> build_lock(build_mu);
 	const double t0 = now_ms();
 	nvrtcProgram prog = nullptr;
 	if (L.CreateProgram(&prog, source.c_str(), "dng_jmatch.cu", 0, nullptr,
@@ -691,9 +701,9 @@ bool jit_build(const std::string &source, int nsl, std::string &cubin,
 		return false;
 	}
 	/* LTO-IR, within the register budget of the kernel it becomes part of
-	 * (__launch_bounds__(768, 1)) */
+	 * (__launch_bounds__(F_NT = 896, 1): 72 registers) */
 	const char *opts[] = { "-arch=sm_100a", "-rdc=true", "-dlto",
-	    "-maxrregcount=80", "-std=c++17", "-lineinfo" };
+	    "-maxrregcount=72", "-std=c++17", "-lineinfo" };
 	const int rc = L.CompileProgram(prog, 6, opts);
 	if (rc != 0) {
 		size_t n = 0;
@@ -715,7 +725,7 @@ bool jit_build(const std::string &source, int nsl, std::string &cubin,
 		*compile_ms = t1 - t0;
 
 	nvJitLinkHandle h = nullptr;
-	const char *lopts[] = { "-arch=sm_100a", "-lto", "-maxrregcount=80",
+	const char *lopts[] = { "-arch=sm_100a", "-lto", "-maxrregcount=72",
 	    "-lineinfo" };
 	if (L.LCreate(&h, 4, lopts) != 0) {
 		err = "nvJitLinkCreate failed";

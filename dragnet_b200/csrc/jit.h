@@ -57,6 +57,10 @@ std::string jit_source(const u8 *blob, size_t bytes, const FPlan *plan,
 std::shared_ptr<JitKernels> jit_request(const std::string &source, int nsl,
     int dev, int smem_max, bool wait);
 
+/* load the two compiler libraries now, on this thread (they are dlopen()ed
+ * once per process); false if they are not there */
+bool jit_prepare();
+
 /* only compile + link, to `cubin` (no device needed: tests); nsl = 16-byte
  * units per lane slice: 7, 9, 11 or 13 */
 bool jit_build(const std::string &source, int nsl, std::string &cubin,

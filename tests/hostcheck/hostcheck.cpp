@@ -235,7 +235,7 @@ int main(int argc, char **argv)
 			if (jm) {
 				/* the record at an odd address of the fake shared
 				 * memory, '\n' and the sentinel quotes after it,
-				 * captures in rows of 768 */
+				 * captures in rows of F_NT */
 				const u32 ra = 1027, caps = 32768;
 				memcpy(jbuf + ra, rec, len);
 				jbuf[ra + len] = '\n';
@@ -244,7 +244,7 @@ int main(int argc, char **argv)
 				matched = r & 1;
 				defmask = r >> 1;
 				for (u32 k = 0; k < F_MAXPATHS; k++)
-					memcpy(&fm.caps[k], jbuf + caps + k * 768 * 4, 4);
+					memcpy(&fm.caps[k], jbuf + caps + k * F_NT * 4, 4);
 			} else {
 				matched = fmatch(fm, len, true, defmask);
 			}

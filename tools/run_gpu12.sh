@@ -1,0 +1,12 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/t_all12.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/t_all12.log
+FLAGS="--steps 5 --warmup 3 --stream-rows 0 --cpu-rows 200000 --cpu-seconds 0.5 --e2e-steps 1 --file-steps 0 --cfg-steps 3 --pool-rows 2000000"
+timeout 600 python bench.py $FLAGS > gpurun_out/bench12.json 2> gpurun_out/bench12.err; echo "bench rc=$?"; tail -2 gpurun_out/bench12.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench12.json').read().strip().splitlines()[-1])
+print('value %.4g'%d['value'],'frac %.4f'%d['roofline']['frac'],'parity',d.get('parity'), d['roofline'].get('kernel'))
+for c in d.get('configs',[]):
+    if c.get('query'): print('   ',c.get('query'),'%.4g'%c.get('value'),c.get('roofline_frac'))
+PY
