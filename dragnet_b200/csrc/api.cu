@@ -197,6 +197,10 @@ struct dng_scan {
 	u8 *d_ftmpl = nullptr;
 	u32 ftmpl_bytes = 0, nftemplates = 0, ftmpl_leaf_off = 0, ftmpl_pool_off = 0;
 	bool f_kernel = false;
+	u32 f_nt = DNG_F_NT;		/* threads of its CTA: DNG_F_NT, or 768 when
+					 * the tally cache needs the shared memory */
+	unsigned long long seen_over = 0, seen_aggr = 0;
+	bool f_probed = false;
 	u32 f_nsl = 13;			/* 16-byte units per lane slice */
 	double mean_line = 224;		/* of the sample the templates came from */
 	u32 f_smem_max = 0;		/* dynamic shared memory a CTA may ask for */
@@ -461,15 +465,16 @@ int learn_templates(dng_scan *s, const u8 *data, unsigned long long start,
 template <int NSL>
 void launch_fkernel(dng_scan *s, const FScanArgs &a, u32 grid)
 {
-	scan_kernel_f<NSL><<<grid, DNG_F_NT, fkernel_smem<NSL>(a.tmpl_bytes,
-	    a.s1slots, a.sslots, a.nrows), s->stream>>>(a);
+	scan_kernel_f<NSL><<<grid, s->f_nt, fkernel_smem<NSL>(a.tmpl_bytes,
+	    a.s1slots, a.sslots, a.nrows, s->f_nt / 32), s->stream>>>(a);
 }
 
 /* tally-cache sizes of the F kernel: what its buffers leave */
 template <int NSL>
 void fkernel_slots(const dng_scan *s, u32 nrows, u32 tmpl_room, u32 *s1, u32 *s2)
 {
-	const size_t fixed = fkernel_smem<NSL>(tmpl_room, 0, 0, nrows);
+	const size_t fixed = fkernel_smem<NSL>(tmpl_room, 0, 0, nrows,
+	    s->f_nt / 32);
 	const size_t room = s->f_smem_max > fixed ? s->f_smem_max - fixed : 0;
 	u32 n1 = 32;
 	while (n1 < 1024 && (size_t)n1 * 2 * sizeof (SSlot1) +
@@ -522,11 +527,12 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 	const u32 nsl = s->f_nsl;
 	const unsigned long long chunk = 32ull * 16 * nsl;
 	a.nchunks = (u32)((nbytes + chunk - 1) / chunk);
-	const u32 grid = std::min<u32>((a.nchunks + DNG_F_NW - 1) / DNG_F_NW,
+	const u32 nw = s->f_nt / 32;
+	const u32 grid = std::min<u32>((a.nchunks + nw - 1) / nw,
 	    (u32)s->sm_count);
 	/* segments: long enough to amortise the pre-lap, short enough to keep
 	 * every warp of the grid busy */
-	const u32 nwarps = grid * DNG_F_NW;
+	const u32 nwarps = grid * nw;
 	a.seg = std::max<u32>(1, std::min<u32>(DNG_F_SEG,
 	    a.nchunks / (nwarps * 8)));
 	/* the segment queue: [1] of the miss counter's allocation */
@@ -545,25 +551,29 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 	switch (nsl) {
 	case 7:
 		fkernel_slots<7>(s, a.nrows, tmpl_room, &a.s1slots, &a.sslots);
-		smem = fkernel_smem<7>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
+		smem = fkernel_smem<7>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows,
+		    s->f_nt / 32);
 		if (!jit)
 			launch_fkernel<7>(s, a, grid);
 		break;
 	case 9:
 		fkernel_slots<9>(s, a.nrows, tmpl_room, &a.s1slots, &a.sslots);
-		smem = fkernel_smem<9>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
+		smem = fkernel_smem<9>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows,
+		    s->f_nt / 32);
 		if (!jit)
 			launch_fkernel<9>(s, a, grid);
 		break;
 	case 11:
 		fkernel_slots<11>(s, a.nrows, tmpl_room, &a.s1slots, &a.sslots);
-		smem = fkernel_smem<11>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
+		smem = fkernel_smem<11>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows,
+		    s->f_nt / 32);
 		if (!jit)
 			launch_fkernel<11>(s, a, grid);
 		break;
 	default:
 		fkernel_slots<13>(s, a.nrows, tmpl_room, &a.s1slots, &a.sslots);
-		smem = fkernel_smem<13>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows);
+		smem = fkernel_smem<13>(a.tmpl_bytes, a.s1slots, a.sslots, a.nrows,
+		    s->f_nt / 32);
 		if (!jit)
 			launch_fkernel<13>(s, a, grid);
 		break;
@@ -572,7 +582,7 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 	if (jit) {
 		void *args[] = { &a };
 		le = cudaLaunchKernel((const void *)s->jit->kern, dim3(grid),
-		    dim3(DNG_F_NT), args, smem, s->stream);
+		    dim3(s->f_nt), args, smem, s->stream);
 		s->jit_launches++;
 	}
 	if (le == cudaSuccess)
@@ -596,12 +606,12 @@ int launch_fscan(dng_scan *s, const u8 *data, unsigned long long start,
 		le = cudaGetLastError();
 	}
 	cudaEventRecord(e1, s->stream);
-	if (!s->h_live && HOST_ALLOC(&s->h_live, 16 * sizeof (unsigned long long))
+	if (!s->h_live && HOST_ALLOC(&s->h_live, NCTR * sizeof (unsigned long long))
 	    == cudaSuccess)
-		memset(s->h_live, 0, 16 * sizeof (unsigned long long));
+		memset(s->h_live, 0, NCTR * sizeof (unsigned long long));
 	if (s->h_live)
 		cudaMemcpyAsync(s->h_live, s->d_counters,
-		    16 * sizeof (unsigned long long), cudaMemcpyDeviceToHost,
+		    NCTR * sizeof (unsigned long long), cudaMemcpyDeviceToHost,
 		    s->stream);
 	s->ev_pairs.emplace_back(e0, e1);
 	s->launches++;
@@ -637,6 +647,15 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 				s->warp_kernel = false;
 			s->seen_lines = lines;
 			s->seen_long = nlong;
+		}
+		/* keys the F kernel's inline tally tier had no room for: with 28
+		 * warps it is small; 24 leave it 30 KB more */
+		if (s->f_nt > 768 && lv[CTR_AGGR] - s->seen_aggr >= 4096) {
+			if ((lv[CTR_OVER] - s->seen_over) * 64 >
+			    lv[CTR_AGGR] - s->seen_aggr)
+				s->f_nt = 768;
+			s->seen_over = lv[CTR_OVER];
+			s->seen_aggr = lv[CTR_AGGR];
 		}
 		const unsigned long long dl = lines - s->learn_lines;
 		/* the F path only pays while it takes nearly every record: with
@@ -706,12 +725,12 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 		    a.s1slots * sizeof (SSlot1), s->stream>>>(a);
 	}
 	cudaEventRecord(e1, s->stream);
-	if (!s->h_live && HOST_ALLOC(&s->h_live, 16 * sizeof (unsigned long long))
+	if (!s->h_live && HOST_ALLOC(&s->h_live, NCTR * sizeof (unsigned long long))
 	    == cudaSuccess)
-		memset(s->h_live, 0, 16 * sizeof (unsigned long long));
+		memset(s->h_live, 0, NCTR * sizeof (unsigned long long));
 	if (s->h_live)
 		cudaMemcpyAsync(s->h_live, s->d_counters,
-		    16 * sizeof (unsigned long long), cudaMemcpyDeviceToHost,
+		    NCTR * sizeof (unsigned long long), cudaMemcpyDeviceToHost,
 		    s->stream);
 	s->ev_pairs.emplace_back(e0, e1);
 	s->launches++;
@@ -928,6 +947,12 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		}
 		/* the F path (fast.h), for the plans it models */
 		fplan_build(plan->dev, s->fplan);
+		/* three columns and more: keys are many more often than not,
+		 * start with the larger tally cache (f_nt) */
+		if (s->fplan.ncols >= 3)
+			s->f_nt = 768;
+		if (const char *ev = getenv("DNG_F_WARPS"))
+			s->f_nt = atoi(ev) >= 28 ? DNG_F_NT : 768;
 		if (getenv("DNG_FAST") && atoi(getenv("DNG_FAST")) == 0)
 			s->fplan.ok = 0;
 		if (const char *ev = getenv("DNG_JIT"))
@@ -1346,6 +1371,22 @@ int dng_scan_feed_device(dng_scan *s, const void *devbuf, size_t len)
 		return 0;
 	}
 	cudaSetDevice(s->device);
+	/*
+	 * A large buffer would be ONE launch: nothing learnt from it could
+	 * help it.  Its head goes first, as a launch of its own, and what that
+	 * one counted (keys that overflowed the F kernel's tally cache: f_nt)
+	 * is looked at before the rest is launched.
+	 */
+	const size_t PROBE = (size_t)64 << 20;
+	if (!s->f_probed && s->fplan.ok && s->f_nt > 768 && len > 4 * PROBE) {
+		s->f_probed = true;
+		int rc = dng_scan_feed_device(s, devbuf, PROBE);
+		if (rc)
+			return rc;
+		CK(s, cudaStreamSynchronize(s->stream));
+		return dng_scan_feed_device(s, (const u8 *)devbuf + PROBE,
+		    len - PROBE);
+	}
 	const u8 *d = (const u8 *)devbuf;
 	s->bytes_fed += len;
 	/* locate the first and last newline (windows first, then all) */

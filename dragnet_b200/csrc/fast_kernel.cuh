@@ -81,13 +81,15 @@ struct FWarpSmem {
 
 static constexpr u32 FPLAN_SMEM = (sizeof (FPlan) + 127) & ~127u;
 
+/* (nw = warps of the launch: DNG_F_NW, or fewer -- the capture rows keep
+ * their stride -- when the tally cache needs the room) */
 template <int NSL>
 static inline size_t fkernel_smem(u32 tmpl_bytes, u32 s1slots, u32 sslots,
-    u32 nrows)
+    u32 nrows, u32 nw = DNG_F_NW)
 {
 	return FPLAN_SMEM + tmpl_bytes + (size_t)s1slots * sizeof (SSlot1) +
 	    (size_t)sslots * sizeof (SSlot) + (size_t)nrows * DNG_F_NT * 4 +
-	    (size_t)DNG_F_NW * FWarpSmem<NSL>::BYTES;
+	    (size_t)nw * FWarpSmem<NSL>::BYTES;
 }
 
 /* mbarrier / TMA helpers on 32-bit shared addresses (no generic pointers to
@@ -293,7 +295,7 @@ __device__ __forceinline__ void sts64_release(u32 addr, unsigned long long v)
  */
 __device__ __forceinline__ void ftally(FSmem &m, const FPlan &F,
     const FPlan *Fcold, u32 defmask, u32 h, u32 klen, const STab &stab,
-    const GTable &gt)
+    const GTable &gt, u32 over_sa)
 {
 	if (klen <= DNG_SKEY) {
 		const unsigned long long claim = (unsigned long long)(h | 1u);
@@ -329,6 +331,8 @@ __device__ __forceinline__ void ftally(FSmem &m, const FPlan &F,
 			idx = (idx + 1) & stab.mask1;
 		}
 	}
+	/* (counted: the host gives the cache more room if this is common) */
+	asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(over_sa) : "memory");
 	fslow_add(m, Fcold, defmask, klen, stab, &gt);
 }
 
@@ -433,17 +437,17 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 	{	/* plan, templates -> shared; clear the tally cache */
 		const uint4 *src = (const uint4 *)a.fplan;
 		uint4 *dst = (uint4 *)smem;
-		for (u32 i = tid; i < FPLAN_SMEM / 16; i += DNG_F_NT)
+		for (u32 i = tid; i < FPLAN_SMEM / 16; i += blockDim.x)
 			dst[i] = src[i];
 		const uint4 *tsrc = (const uint4 *)a.tmpl;
 		uint4 *tdst = (uint4 *)(smem + FPLAN_SMEM);
-		for (u32 i = tid; i < a.tmpl_bytes / 16; i += DNG_F_NT)
+		for (u32 i = tid; i < a.tmpl_bytes / 16; i += blockDim.x)
 			tdst[i] = tsrc[i];
 		const uint4 z = make_uint4(0, 0, 0, 0);
 		uint4 *tz = (uint4 *)stab.s1;
 		const u32 tab_bytes = a.s1slots * (u32)sizeof (SSlot1) +
 		    a.sslots * (u32)sizeof (SSlot);
-		for (u32 i = tid; i < tab_bytes / 16; i += DNG_F_NT)
+		for (u32 i = tid; i < tab_bytes / 16; i += blockDim.x)
 			tz[i] = z;
 		if (lane == 0)
 			mbar_init_sa(mbar, 1);
@@ -477,7 +481,7 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 	 * at the final barrier).  The first round is implicit -- warp gw takes
 	 * segment gw, spread over the SMs -- the counter hands out the rest.
 	 */
-	const u32 nwarps = gridDim.x * DNG_F_NW;
+	const u32 nwarps = gridDim.x * (blockDim.x >> 5);
 	const u32 gw = wid * gridDim.x + blockIdx.x;
 	const u32 nseg = (a.nchunks + a.seg - 1) / a.seg;
 
@@ -716,7 +720,8 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 							if (slow)
 								atomicAdd(&s_drop[1], 1u);
 							ftally(m, F, (const FPlan *)smem, defmask,
-							    h, klen, stab, a.tab);
+							    h, klen, stab, a.tab,
+							    smem_u32(&s_drop[15]));
 						}
 					}
 					const bool done = fo != FO_MISS;
@@ -790,7 +795,9 @@ __device__ __forceinline__ void fscan_body(const FScanArgs &a)
 		if (naggr)
 			atomicAdd(&a.counters[CTR_AGGR], (unsigned long long)naggr);
 	}
-	if (tid < 16 && s_drop[tid]) {
+	if (tid == 15 && s_drop[15])
+		atomicAdd(&a.counters[CTR_OVER], (unsigned long long)s_drop[15]);
+	if (tid < 15 && s_drop[tid]) {
 		/* FO_* -> CTR_*; s_drop[1] = records that took a slow conversion */
 		const int ctr = tid == 1 ? (int)CTR_SLOW :
 		    tid == FO_DS_FILTERED ? (int)CTR_DS_FILTERED :

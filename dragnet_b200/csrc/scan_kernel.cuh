@@ -69,7 +69,8 @@ enum {
 	CTR_LINES = 0, CTR_INVALID_JSON, CTR_INVALID_POINT,
 	CTR_DS_FILTERED, CTR_DS_FAILED, CTR_USER_FILTERED, CTR_USER_FAILED,
 	CTR_SYNTH_UNDEF, CTR_SYNTH_BADDATE, CTR_TIME_FILTERED, CTR_TIME_FAILED,
-	CTR_AGGR, CTR_SLOW, CTR_UNSUPPORTED, CTR_LONG, CTR_TMPL
+	CTR_AGGR, CTR_SLOW, CTR_UNSUPPORTED, CTR_LONG, CTR_TMPL,
+	CTR_OVER	/* F kernel: keys its inline tally tier had no room for */
 };
 
 enum { ST_TABLE_FULL = 1, ST_ARENA_FULL = 2 };
