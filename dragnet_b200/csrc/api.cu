@@ -269,6 +269,29 @@ __global__ void resolve_pairs_kernel(const DevPlan *plan, const u8 *lines,
  * by path, compact literals.  The F kernel is chosen when they cover the
  * sample (results never depend on that choice, only the speed does).
  */
+/*
+ * What a scan of this plan found out about its tally cache (f_nt), kept for
+ * the scans of the same plan that follow in this process: they start with it
+ * and need no probe launch.
+ */
+static std::mutex g_fnt_mu;
+static std::map<unsigned long long, u32> g_fnt_memo;
+
+static unsigned long long fplan_hash(const FPlan &F)
+{
+	unsigned long long h = 1469598103934665603ull;
+	const u8 *p = (const u8 *)&F;
+	for (size_t i = 0; i < sizeof (F); i++)
+		h = (h ^ p[i]) * 1099511628211ull;
+	return h;
+}
+
+static void fnt_remember(const dng_scan *s)
+{
+	std::lock_guard<std::mutex> g(g_fnt_mu);
+	g_fnt_memo[fplan_hash(s->fplan)] = s->f_nt;
+}
+
 int learn_ftemplates(dng_scan *s, const std::vector<TCandidate> &cands,
     const std::vector<TResolved> &res, size_t sampled_lines)
 {
@@ -656,6 +679,7 @@ int launch_scan(dng_scan *s, const u8 *data, unsigned long long start,
 				s->f_nt = 768;
 			s->seen_over = lv[CTR_OVER];
 			s->seen_aggr = lv[CTR_AGGR];
+			fnt_remember(s);
 		}
 		const unsigned long long dl = lines - s->learn_lines;
 		/* the F path only pays while it takes nearly every record: with
@@ -951,8 +975,18 @@ int dng_scan_open(const dng_plan *plan, int device, dng_scan **out, char *err,
 		 * start with the larger tally cache (f_nt) */
 		if (s->fplan.ncols >= 3)
 			s->f_nt = 768;
-		if (const char *ev = getenv("DNG_F_WARPS"))
+		{
+			std::lock_guard<std::mutex> g(g_fnt_mu);
+			auto it = g_fnt_memo.find(fplan_hash(s->fplan));
+			if (it != g_fnt_memo.end()) {
+				s->f_nt = it->second;
+				s->f_probed = true;
+			}
+		}
+		if (const char *ev = getenv("DNG_F_WARPS")) {
 			s->f_nt = atoi(ev) >= 28 ? DNG_F_NT : 768;
+			s->f_probed = true;
+		}
 		if (getenv("DNG_FAST") && atoi(getenv("DNG_FAST")) == 0)
 			s->fplan.ok = 0;
 		if (const char *ev = getenv("DNG_JIT"))
