@@ -78,6 +78,22 @@ def make_plan(qconf, ds=None):
                                time_field=ds.get('timeField'))
 
 
+def kernel_sources_sha16():
+    """What the library is built from (dragnet_b200/csrc), as a digest: ties a
+    stored ncu capture (profiles/r2_traffic.json) to the kernel it was taken
+    on."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'dragnet_b200', 'csrc')
+    for p in sorted(glob.glob(os.path.join(d, '*'))):
+        if os.path.isfile(p) and (os.path.splitext(p)[1] in (
+                '.cu', '.cuh', '.cpp', '.h', '.S') or p.endswith('Makefile')):
+            h.update(os.path.basename(p).encode())
+            h.update(open(p, 'rb').read())
+    return h.hexdigest()[:16]
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -686,14 +702,16 @@ def gpu_arm(args, rank, local_rank, world):
     kname = kernel_name(st)
     # DRAM traffic of the scan kernel: from the `ncu --set full` capture of
     # this very command kept in profiles/ (bench.py cannot run under ncu); only
-    # used if it was taken of the kernel this run launched
+    # used if it was taken of the kernel this run launched, on this query,
+    # built from these very sources (kernel_sources_sha16): null otherwise
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
             if tj.get('kernel') == kname.split(' ')[0] and \
-                    tj.get('query') == args.query:
+                    tj.get('query') == args.query and \
+                    tj.get('sources_sha16') == kernel_sources_sha16():
                 traffic = tj['traffic_over_algorithmic'] * \
                     (R['kernel_bytes'] / n_launch)
                 traffic_src = ('dram__bytes_read.sum + dram__bytes_write.sum '

@@ -86,7 +86,11 @@ summ['r2_final_C3_100M_rows'] = {
     'dram_traffic_over_algorithmic': (rd + wr) / alg,
 }
 json.dump(summ, open(os.path.join(P, 'r2_ncu_summary.json'), 'w'), indent=1)
+import sys
+sys.path.insert(0, ROOT)
+import bench
 json.dump({'kernel': 'dng_scan_kernel_j', 'query': 'C3', 'rows': NREC, 'algorithmic_bytes': alg,
+           'sources_sha16': bench.kernel_sources_sha16(),
            'dram_bytes_read': rd, 'dram_bytes_write': wr,
            'traffic_over_algorithmic': (rd + wr) / alg,
            'source': 'ncu --set full capture of the bench launch (profiles/r2_ncu_summary.json r2_final_C3_100M_rows)'},

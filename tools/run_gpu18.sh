@@ -1,0 +1,11 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_feeds.py -x -q -m gpu 2>&1 | tail -2
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 --stream-rows 0 --cfg-steps 1 --cpu-seconds 0.5 --cpu-rows 200000 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 rc=$?"
+tail -2 gpurun_out/bench_n2.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_n2.json').read().strip().splitlines()[-1])
+print({k:d.get(k) for k in ('value','n_gpus','ms_per_step','parity','merge_parity','scaling')}, d['roofline']['frac'], d['e2e'].get('value'), d['e2e'].get('parity'))
+PY
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 2>/dev/null | tail -1 | cut -c1-300
