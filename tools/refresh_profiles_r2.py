@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Round-2 evidence: raw outputs of tools/run_gpu17.sh (gpurun_out/) -> the
+"""Round-2 evidence: raw outputs of tools/gpu_evidence.sh (gpurun_out/) -> the
 tracked summaries under profiles/r2_*.  The run, on the GPU box:
 
   python bench.py                         > gpurun_out/bench_r2_n1.json
@@ -77,7 +77,7 @@ alg = float(b['roofline']['bytes_per_launch'])
 rd, wr = to_bytes(metrics['dram__bytes_read.sum']), to_bytes(metrics['dram__bytes_write.sum'])
 summ = json.load(open(os.path.join(P, 'r2_ncu_summary.json')))
 summ['r2_final_C3_100M_rows'] = {
-    'command': 'ncu --set full --clock-control none --import-source on -k regex:dng_scan_kernel_j -s 3 -c 1 python bench.py ... (tools/run_gpu17.sh)',
+    'command': 'ncu --set full --clock-control none --import-source on -k regex:dng_scan_kernel_j -s 3 -c 1 python bench.py ... (tools/gpu_evidence.sh)',
     'kernel': 'dng_scan_kernel_j (scan_kernel_f, 28 warps of 72 registers, linked at run time with the matcher generated for the 3 learned templates; plan constant-folded)',
     'query': 'C3: ' + b['config']['query'],
     'records': NREC, 'algorithmic_bytes': alg, 'metrics': metrics,
