@@ -217,6 +217,7 @@ BASELINE_QUERIES = {
                 '{"ne":["req.caller","admin"]}'], None),
     'lq': (['-b', 'dataLatency[aggr=lquantize,step=100],host'], None),
     'url': (['-b', 'req.url'], None),
+    'urlhost': (['-b', 'req.url,host'], None),
 }
 
 
