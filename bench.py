@@ -607,6 +607,8 @@ def gpu_arm(args, rank, local_rank, world):
     # ---- the other BASELINE configs, resident in HBM ---------------------------
     configs = []
     for q in ('C2', 'C3', 'C4', 'C5'):
+        if q != args.query and args.cfg_steps <= 0:
+            continue
         C = R if q == args.query else timed(feed_resident, args.cfg_steps, 1,
                                             q=q)
         steps = args.steps if q == args.query else args.cfg_steps

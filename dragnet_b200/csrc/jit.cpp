@@ -42,6 +42,7 @@ const char *PRELUDE =
 "#ifdef DNG_JIT_SHARED_SCAN\n"
 "#define DNG_FSCAN_FN __device__ __noinline__\n"
 "#endif\n"
+
 "enum { T_UNDEF = 0, T_NULL = 1, T_FALSE = 2, T_TRUE = 3, T_NUM = 4, T_STR = 5 };\n"
 "#define DNG_FCAP(type, off, len, flag) \\\n"
 "	((u32)(off) | ((u32)(len) << 12) | ((u32)(type) << 24) | ((u32)(flag) << 27))\n"
@@ -248,13 +249,21 @@ std::string jit_source(const u8 *blob, size_t bytes, const FPlan *plan,
 {
 	std::string s;
 	s += "/* generated by libdragnet_gpu (jit.cpp) */\n";
-	/* DNG_JIT_SHARED=1: one copy of each scanner, called, instead of one
-	 * inlined into every block.  Measured on B200 (100 M rows, configs[2]):
-	 * the kernel shrinks from 37 KB to 28 KB of hot code and gets 13 %
-	 * slower (81 instead of 74 warp-instructions per record, and the
-	 * returns stall the instruction fetch), so it is off. */
-	const char *sh = getenv("DNG_JIT_SHARED");
-	if (!prelude && sh && atoi(sh) == 1)
+	/*
+	 * One copy of each scanner, called, instead of one inlined into every
+	 * block?  Measured on B200 (100 M rows): with one or two columns the
+	 * kernel's loop is 37 KB of code against 32 KB of instruction cache and
+	 * the calls cost more than the misses they save (configs[2]: -7 %);
+	 * with three columns the unrolled key code makes it 40 KB, the hit rate
+	 * falls from 84 % to 62 %, the L1.5's fetch rate becomes the bound and
+	 * the shared copies win (configs[4]: +13 %).  (Sharing the number
+	 * scanner alone: -2 % and -4 % on configs[2] and [1].)
+	 * DNG_JIT_SHARED=0|1 forces.
+	 */
+	bool shared = plan && plan->ncols >= 3;
+	if (const char *sh = getenv("DNG_JIT_SHARED"))
+		shared = atoi(sh) == 1;
+	if (!prelude && shared)
 		s += "#define DNG_JIT_SHARED_SCAN\n";
 	s += prelude ? prelude : PRELUDE;
 	if (plan)
