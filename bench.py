@@ -38,6 +38,13 @@ import tempfile
 import threading
 import time
 
+# torch is plumbing here (device buffers, NCCL): left alone it starts one OpenMP
+# thread per CPU it sees (128 on the B200 hosts) and their spin-waiting eats the
+# container's CPU quota (16-24 CPUs) -- the file readers of the e2e_file leg
+# were throttled to a tenth of their speed by it
+os.environ.setdefault('OMP_NUM_THREADS', '4')
+os.environ.setdefault('MKL_NUM_THREADS', '4')
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
