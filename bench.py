@@ -599,7 +599,11 @@ def gpu_arm(args, rank, local_rank, world):
     # ---- files: the same pool as a tmpfs file through dng_scan_feed_file -------
     file_leg = None
     if world == 1 and args.file_steps > 0:
+        if os.environ.get('DNG_BENCH_TRACE'):
+            sys.stderr.write('TRACE file leg begins %.3f\n' % time.time())
         Fr = timed(lambda s: s.feed_file(pool_path), args.file_steps, 1)
+        if os.environ.get('DNG_BENCH_TRACE'):
+            sys.stderr.write('TRACE file leg ends %.3f\n' % time.time())
         fms = Fr['dev_ms'] / args.file_steps
         file_leg = {'value': pool_rows / (fms / 1e3),
                     'unit': 'records/s', 'ms_per_step': fms,
