@@ -609,6 +609,8 @@ def gpu_arm(args, rank, local_rank, world):
                     'unit': 'records/s', 'ms_per_step': fms,
                     'file_bytes': pool_len,
                     'gbs': pool_len / 1e9 / (fms / 1e3),
+                    'kernel_ms_per_step': Fr['kernel_ms'] / args.file_steps,
+                    'launches_per_step': Fr['launches'] / args.file_steps,
                     'parity': 'exact' if as_dict(Fr['last'][0]) == pool_exp
                     else 'MISMATCH',
                     'note': 'dng_scan_feed_file on a page-cache-resident '

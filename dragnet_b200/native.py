@@ -175,7 +175,12 @@ class Plan(object):
             lib().dng_plan_destroy(self.handle)
             self.handle = _P()
 
-    __del__ = close
+    def __del__(self):
+        # (at interpreter exit the module's globals may be gone already)
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Result(object):
@@ -240,7 +245,12 @@ class Result(object):
             lib().dng_result_destroy(self.handle)
             self.handle = _P()
 
-    __del__ = close
+    def __del__(self):
+        # (at interpreter exit the module's globals may be gone already)
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def result_from_points(plan, points):
@@ -375,7 +385,12 @@ class Scan(object):
             lib().dng_scan_destroy(self.handle)
             self.handle = _P()
 
-    __del__ = close
+    def __del__(self):
+        # (at interpreter exit the module's globals may be gone already)
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def gen_params(seed=0xD5A60000, total_records=1000, string_latency=False,
