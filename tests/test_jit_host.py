@@ -43,3 +43,35 @@ def test_generated_matcher_builds_for_the_device_and_matches(tmp_path,
     act_p, act_c = hostcheck_engine(plan, [str(p)])
     assert canon_points(act_p) == canon_points(exp_p)
     assert act_c == exp_c
+
+
+def test_three_column_plans_link_with_shared_scanners(tmp_path):
+    """Plans of three columns and more get the wildcard scanners as shared,
+    called copies (jit.cpp: their loop does not fit the instruction cache
+    otherwise); that source must build and link for the device, and the linked
+    code must really hold the two functions."""
+    from dragnet_b200 import native
+    n = 2000
+    data = native.gen_host(native.gen_params(total_records=n), 0, n)
+    p = tmp_path / 'syn.log'
+    p.write_bytes(data)
+    exe = build_hostcheck()
+    for argv, shared in ((['-b', 'operation,req.method,host'], True),
+                         (['-b', 'req.method,host'], False)):
+        plan = corpus.make_plan(argv)
+        pf = tmp_path / 'plan.json'
+        pf.write_text(json.dumps(plan))
+        dump = str(tmp_path / 'jm')
+        env = dict(os.environ, DNG_HOSTCHECK_F='1', DNG_HOSTCHECK_JIT='2',
+                   DNG_HOSTCHECK_JIT_DUMP=dump)
+        env.pop('DNG_JIT_SHARED', None)
+        r = subprocess.run([exe, str(pf), str(p)], capture_output=True,
+                           env=env)
+        assert r.returncode == 0, r.stderr.decode()
+        src = open(dump + '.cu').read()
+        assert ('#define DNG_JIT_SHARED_SCAN' in src) == shared
+        sass = subprocess.run(['cuobjdump', '-sass', dump + '.cubin'],
+                              capture_output=True, text=True).stdout
+        fns = [l for l in sass.splitlines() if 'Function :' in l]
+        assert any('fscan_str_p' in l for l in fns) == shared
+        assert any('fscan_bare_p' in l for l in fns) == shared
